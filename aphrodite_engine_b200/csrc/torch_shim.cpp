@@ -1,0 +1,357 @@
+// torch_shim.cpp — the drop-in seam: registers the reference's torch ops (same namespaces, same
+// schemas, same mutability annotations as kernels/torch_bindings.cpp:19-535 of the reference) and
+// forwards each to the C ABI of libb200decode.so (include/b200_decode.h).
+//
+// Built as `_C.abi3.so` with PyInit__C, so `import aphrodite._C` (aphrodite/_custom_ops.py:13-24)
+// can load this file in place of the reference's extension, or it can be injected with
+// torch.ops.load_library() from an `aphrodite.general_plugins` entry point.
+// Only marshalling lives here: device guard, current stream, strides, dtype codes, error mapping
+// (non-zero C-ABI status -> c10::Error -> Python RuntimeError, like the reference's TORCH_CHECK).
+#include <Python.h>
+
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <torch/all.h>
+#include <torch/library.h>
+
+#include <string>
+#include <vector>
+
+#include "b200_decode.h"
+
+namespace {
+
+inline int dtype_code(const torch::Tensor& t, const char* what) {
+  switch (t.scalar_type()) {
+    case at::ScalarType::Float: return B200_F32;
+    case at::ScalarType::Half: return B200_F16;
+    case at::ScalarType::BFloat16: return B200_BF16;
+    default: TORCH_CHECK(false, what, ": unsupported dtype ", t.scalar_type());
+  }
+  return -1;
+}
+
+inline int kv_code(const std::string& s) {
+  const int c = b200_parse_kv_cache_dtype(s.c_str());
+  TORCH_CHECK(c >= 0, "Unsupported data type of kv cache: ", s);
+  return c;
+}
+
+inline void check(int rc) { TORCH_CHECK(rc == 0, b200_last_error()); }
+
+inline void* cur_stream() { return (void*)at::cuda::getCurrentCUDAStream().stream(); }
+
+// ---- attention -----------------------------------------------------------------------------
+void paged_attention_v1(torch::Tensor& out, torch::Tensor& query, torch::Tensor& key_cache,
+                        torch::Tensor& value_cache, int64_t num_kv_heads, double scale,
+                        torch::Tensor& block_tables, torch::Tensor& seq_lens, int64_t block_size,
+                        int64_t max_seq_len, const c10::optional<torch::Tensor>& alibi_slopes,
+                        const std::string& kv_cache_dtype, double k_scale, double v_scale,
+                        const int64_t tp_rank, const int64_t blocksparse_local_blocks,
+                        const int64_t blocksparse_vert_stride,
+                        const int64_t blocksparse_block_size,
+                        const int64_t blocksparse_head_sliding_step) {
+  const at::cuda::OptionalCUDAGuard guard(device_of(query));
+  TORCH_CHECK(block_tables.scalar_type() == at::kInt && seq_lens.scalar_type() == at::kInt,
+              "block_tables and seq_lens must be int32");
+  check(b200_paged_attention_v1(
+      out.data_ptr(), query.data_ptr(), key_cache.data_ptr(), value_cache.data_ptr(),
+      (int)query.size(0), (int)query.size(1), (int)num_kv_heads, (int)query.size(2),
+      (int)block_size, (float)scale, block_tables.data_ptr<int>(), seq_lens.data_ptr<int>(),
+      (int)block_tables.size(1), (int)max_seq_len,
+      alibi_slopes ? reinterpret_cast<const float*>(alibi_slopes.value().data_ptr()) : nullptr,
+      query.stride(0), key_cache.stride(0), key_cache.stride(1), dtype_code(query, "query"),
+      kv_code(kv_cache_dtype), (float)k_scale, (float)v_scale, (int)tp_rank,
+      (int)blocksparse_local_blocks, (int)blocksparse_vert_stride, (int)blocksparse_block_size,
+      (int)blocksparse_head_sliding_step, cur_stream()));
+}
+
+void paged_attention_v2(torch::Tensor& out, torch::Tensor& exp_sums, torch::Tensor& max_logits,
+                        torch::Tensor& tmp_out, torch::Tensor& query, torch::Tensor& key_cache,
+                        torch::Tensor& value_cache, int64_t num_kv_heads, double scale,
+                        torch::Tensor& block_tables, torch::Tensor& seq_lens, int64_t block_size,
+                        int64_t max_seq_len, const c10::optional<torch::Tensor>& alibi_slopes,
+                        const std::string& kv_cache_dtype, double k_scale, double v_scale,
+                        const int64_t tp_rank, const int64_t blocksparse_local_blocks,
+                        const int64_t blocksparse_vert_stride,
+                        const int64_t blocksparse_block_size,
+                        const int64_t blocksparse_head_sliding_step) {
+  const at::cuda::OptionalCUDAGuard guard(device_of(query));
+  TORCH_CHECK(block_tables.scalar_type() == at::kInt && seq_lens.scalar_type() == at::kInt,
+              "block_tables and seq_lens must be int32");
+  check(b200_paged_attention_v2(
+      out.data_ptr(), exp_sums.data_ptr<float>(), max_logits.data_ptr<float>(), tmp_out.data_ptr(),
+      query.data_ptr(), key_cache.data_ptr(), value_cache.data_ptr(), (int)query.size(0),
+      (int)query.size(1), (int)num_kv_heads, (int)query.size(2), (int)block_size, (float)scale,
+      block_tables.data_ptr<int>(), seq_lens.data_ptr<int>(), (int)block_tables.size(1),
+      (int)max_seq_len, (int)exp_sums.size(2),
+      alibi_slopes ? reinterpret_cast<const float*>(alibi_slopes.value().data_ptr()) : nullptr,
+      query.stride(0), key_cache.stride(0), key_cache.stride(1), dtype_code(query, "query"),
+      kv_code(kv_cache_dtype), (float)k_scale, (float)v_scale, (int)tp_rank,
+      (int)blocksparse_local_blocks, (int)blocksparse_vert_stride, (int)blocksparse_block_size,
+      (int)blocksparse_head_sliding_step, cur_stream()));
+}
+
+// ---- activations / norm / rotary --------------------------------------------------------------
+template <int ACT>
+void act_and_mul(torch::Tensor& out, torch::Tensor& input) {
+  const at::cuda::OptionalCUDAGuard guard(device_of(input));
+  const int d = (int)(input.size(-1) / 2);
+  const int64_t tokens = input.numel() / input.size(-1);
+  check(b200_act_and_mul(out.data_ptr(), input.data_ptr(), (int)tokens, d, ACT,
+                         dtype_code(input, "act_and_mul"), cur_stream()));
+}
+template <int ACT>
+void activation(torch::Tensor& out, torch::Tensor& input) {
+  const at::cuda::OptionalCUDAGuard guard(device_of(input));
+  const int d = (int)input.size(-1);
+  const int64_t tokens = input.numel() / d;
+  check(b200_activation(out.data_ptr(), input.data_ptr(), (int)tokens, d, ACT,
+                        dtype_code(input, "activation"), cur_stream()));
+}
+
+void rms_norm(torch::Tensor& out, torch::Tensor& input, torch::Tensor& weight, double epsilon) {
+  const at::cuda::OptionalCUDAGuard guard(device_of(input));
+  const int hidden = (int)input.size(-1);
+  check(b200_rms_norm(out.data_ptr(), input.data_ptr(), weight.data_ptr(), (float)epsilon,
+                      (int)(input.numel() / hidden), hidden, dtype_code(input, "rms_norm"),
+                      cur_stream()));
+}
+
+void fused_add_rms_norm(torch::Tensor& input, torch::Tensor& residual, torch::Tensor& weight,
+                        double epsilon) {
+  const at::cuda::OptionalCUDAGuard guard(device_of(input));
+  const int hidden = (int)input.size(-1);
+  check(b200_fused_add_rms_norm(input.data_ptr(), residual.data_ptr(), weight.data_ptr(),
+                                (float)epsilon, (int)(input.numel() / hidden), hidden,
+                                dtype_code(input, "fused_add_rms_norm"), cur_stream()));
+}
+
+void rotary_embedding(torch::Tensor& positions, torch::Tensor& query, torch::Tensor& key,
+                      int64_t head_size, torch::Tensor& cos_sin_cache, bool is_neox) {
+  const at::cuda::OptionalCUDAGuard guard(device_of(query));
+  const int64_t num_tokens = query.numel() / query.size(-1);
+  check(b200_rotary_embedding(
+      positions.data_ptr<int64_t>(), query.data_ptr(), key.data_ptr(), cos_sin_cache.data_ptr(),
+      nullptr, (int)num_tokens, (int)(query.size(-1) / head_size), (int)(key.size(-1) / head_size),
+      (int)head_size, (int)cos_sin_cache.size(1), query.stride(-2), key.stride(-2), is_neox ? 1 : 0,
+      dtype_code(query, "rotary_embedding"), cur_stream()));
+}
+
+void batched_rotary_embedding(torch::Tensor& positions, torch::Tensor& query, torch::Tensor& key,
+                              int64_t head_size, torch::Tensor& cos_sin_cache, bool is_neox,
+                              int64_t rot_dim, torch::Tensor& cos_sin_cache_offsets) {
+  const at::cuda::OptionalCUDAGuard guard(device_of(query));
+  const int64_t num_tokens = cos_sin_cache_offsets.size(0);
+  check(b200_rotary_embedding(
+      positions.data_ptr<int64_t>(), query.data_ptr(), key.data_ptr(), cos_sin_cache.data_ptr(),
+      cos_sin_cache_offsets.data_ptr<int64_t>(), (int)num_tokens,
+      (int)(query.size(-1) / head_size), (int)(key.size(-1) / head_size), (int)head_size,
+      (int)rot_dim, query.stride(-2), key.stride(-2), is_neox ? 1 : 0,
+      dtype_code(query, "batched_rotary_embedding"), cur_stream()));
+}
+
+// ---- cache ops ------------------------------------------------------------------------------------
+void swap_blocks(torch::Tensor& src, torch::Tensor& dst, const torch::Tensor& block_mapping) {
+  const torch::Device sd = src.device(), dd = dst.device();
+  int kind;
+  if (sd.is_cuda() && dd.is_cuda()) {
+    TORCH_CHECK(sd.index() == dd.index(), "src and dst must be on the same GPU");
+    kind = 0;
+  } else if (sd.is_cuda() && dd.is_cpu()) {
+    kind = 1;
+  } else if (sd.is_cpu() && dd.is_cuda()) {
+    kind = 2;
+  } else {
+    TORCH_CHECK(false, "Invalid device combination");
+  }
+  TORCH_CHECK(block_mapping.device().is_cpu(), "block_mapping must be on CPU");
+  TORCH_CHECK(block_mapping.scalar_type() == at::kLong, "block_mapping must be int64");
+  const torch::Tensor bm = block_mapping.contiguous();
+  const int64_t block_bytes = src.element_size() * src[0].numel();
+  const at::cuda::OptionalCUDAGuard guard(sd.is_cuda() ? sd : dd);
+  check(b200_swap_blocks(src.data_ptr(), dst.data_ptr(), bm.data_ptr<int64_t>(), (int)bm.size(0),
+                         block_bytes, kind, cur_stream()));
+}
+
+void copy_blocks(std::vector<torch::Tensor> const& key_caches,
+                 std::vector<torch::Tensor> const& value_caches,
+                 const torch::Tensor& block_mapping) {
+  const int num_layers = (int)key_caches.size();
+  TORCH_CHECK(num_layers == (int)value_caches.size());
+  if (num_layers == 0) return;
+  const torch::Device dev = key_caches[0].device();
+  TORCH_CHECK(dev.is_cuda());
+  std::vector<int64_t> kp(num_layers), vp(num_layers);
+  for (int i = 0; i < num_layers; ++i) {
+    kp[i] = reinterpret_cast<int64_t>(key_caches[i].data_ptr());
+    vp[i] = reinterpret_cast<int64_t>(value_caches[i].data_ptr());
+  }
+  // same host->device hand-off of the pointer tables as the reference (cache_kernels.cu:128-133)
+  torch::Tensor kpt = torch::from_blob(kp.data(), {num_layers}, torch::kInt64).to(dev);
+  torch::Tensor vpt = torch::from_blob(vp.data(), {num_layers}, torch::kInt64).to(dev);
+  const int64_t block_bytes = key_caches[0][0].numel() * key_caches[0].element_size();
+  const at::cuda::OptionalCUDAGuard guard(dev);
+  check(b200_copy_blocks(kpt.data_ptr<int64_t>(), vpt.data_ptr<int64_t>(),
+                         block_mapping.data_ptr<int64_t>(), num_layers, (int)block_mapping.size(0),
+                         block_bytes, cur_stream()));
+}
+
+void reshape_and_cache(torch::Tensor& key, torch::Tensor& value, torch::Tensor& key_cache,
+                       torch::Tensor& value_cache, torch::Tensor& slot_mapping,
+                       const std::string& kv_cache_dtype, const double k_scale,
+                       const double v_scale) {
+  const at::cuda::OptionalCUDAGuard guard(device_of(key));
+  check(b200_reshape_and_cache(
+      key.data_ptr(), value.data_ptr(), key_cache.data_ptr(), value_cache.data_ptr(),
+      slot_mapping.data_ptr<int64_t>(), (int)key.size(0), (int)key.size(1), (int)key.size(2),
+      (int)key_cache.size(3), (int)key_cache.size(4), key.stride(0), value.stride(0),
+      dtype_code(key, "Unsupported input type of kv cache"), kv_code(kv_cache_dtype),
+      (float)k_scale, (float)v_scale, cur_stream()));
+}
+
+void reshape_and_cache_flash(torch::Tensor& key, torch::Tensor& value, torch::Tensor& key_cache,
+                             torch::Tensor& value_cache, torch::Tensor& slot_mapping,
+                             const std::string& kv_cache_dtype, const double k_scale,
+                             const double v_scale) {
+  const at::cuda::OptionalCUDAGuard guard(device_of(key));
+  TORCH_CHECK(key_cache.stride(0) == value_cache.stride(0));
+  check(b200_reshape_and_cache_flash(
+      key.data_ptr(), value.data_ptr(), key_cache.data_ptr(), value_cache.data_ptr(),
+      slot_mapping.data_ptr<int64_t>(), (int)key.size(0), (int)key.size(1), (int)key.size(2),
+      (int)key_cache.size(1), key_cache.stride(0), key.stride(0), value.stride(0),
+      dtype_code(key, "Unsupported input type of kv cache"), kv_code(kv_cache_dtype),
+      (float)k_scale, (float)v_scale, cur_stream()));
+}
+
+void convert_fp8(torch::Tensor& dst_cache, torch::Tensor& src_cache, const double scale,
+                 const std::string& kv_cache_dtype) {
+  TORCH_CHECK(src_cache.device().is_cuda(), "src must be on a GPU");
+  TORCH_CHECK(dst_cache.device().is_cuda(), "dst must be on a GPU");
+  TORCH_CHECK(src_cache.device().index() == dst_cache.device().index(),
+              "src and dst must be on the same GPU");
+  const at::cuda::OptionalCUDAGuard guard(src_cache.device());
+  auto code = [](const torch::Tensor& t) {
+    switch (t.scalar_type()) {
+      case at::ScalarType::Float: return (int)B200_F32;
+      case at::ScalarType::Half: return (int)B200_F16;
+      case at::ScalarType::BFloat16: return (int)B200_BF16;
+      default: return -1;  // uint8 fp8 storage
+    }
+  };
+  TORCH_CHECK(kv_cache_dtype == "auto" || kv_cache_dtype == "fp8" || kv_cache_dtype == "fp8_e4m3",
+              "Unsupported data type: ", kv_cache_dtype);
+  check(b200_convert_fp8(dst_cache.data_ptr(), src_cache.data_ptr(), src_cache.numel(),
+                         code(src_cache), code(dst_cache), kv_code(kv_cache_dtype), (float)scale,
+                         cur_stream()));
+}
+
+int64_t get_device_attribute(int64_t attribute, int64_t device_id) {
+  return b200_get_device_attribute(attribute, device_id);
+}
+int64_t get_max_shared_memory_per_block_device_attribute(int64_t device_id) {
+  return b200_get_max_shared_memory_per_block_device_attribute(device_id);
+}
+
+}  // namespace
+
+TORCH_LIBRARY(_C, ops) {
+  ops.def(
+      "paged_attention_v1("
+      "    Tensor! out, Tensor query, Tensor key_cache,"
+      "    Tensor value_cache, int num_kv_heads, float scale,"
+      "    Tensor block_tables, Tensor seq_lens, int block_size,"
+      "    int max_seq_len, Tensor? alibi_slopes,"
+      "    str kv_cache_dtype, float k_scale, float v_scale,"
+      "    int tp_rank, int blocksparse_local_blocks,"
+      "    int blocksparse_vert_stride, int blocksparse_block_size,"
+      "    int blocksparse_head_sliding_step) -> ()");
+  ops.impl("paged_attention_v1", torch::kCUDA, &paged_attention_v1);
+  ops.def(
+      "paged_attention_v2("
+      "    Tensor! out, Tensor! exp_sums, Tensor! max_logits,"
+      "    Tensor! tmp_out, Tensor query, Tensor key_cache,"
+      "    Tensor value_cache, int num_kv_heads, float scale,"
+      "    Tensor block_tables, Tensor seq_lens, int block_size,"
+      "    int max_seq_len, Tensor? alibi_slopes,"
+      "    str kv_cache_dtype, float k_scale, float v_scale,"
+      "    int tp_rank, int blocksparse_local_blocks,"
+      "    int blocksparse_vert_stride, int blocksparse_block_size,"
+      "    int blocksparse_head_sliding_step) -> ()");
+  ops.impl("paged_attention_v2", torch::kCUDA, &paged_attention_v2);
+
+  ops.def("silu_and_mul(Tensor! out, Tensor input) -> ()");
+  ops.impl("silu_and_mul", torch::kCUDA, &act_and_mul<0>);
+  ops.def("gelu_and_mul(Tensor! out, Tensor input) -> ()");
+  ops.impl("gelu_and_mul", torch::kCUDA, &act_and_mul<1>);
+  ops.def("gelu_tanh_and_mul(Tensor! out, Tensor input) -> ()");
+  ops.impl("gelu_tanh_and_mul", torch::kCUDA, &act_and_mul<2>);
+  ops.def("gelu_new(Tensor! out, Tensor input) -> ()");
+  ops.impl("gelu_new", torch::kCUDA, &activation<0>);
+  ops.def("gelu_fast(Tensor! out, Tensor input) -> ()");
+  ops.impl("gelu_fast", torch::kCUDA, &activation<1>);
+  ops.def("gelu_quick(Tensor! out, Tensor input) -> ()");
+  ops.impl("gelu_quick", torch::kCUDA, &activation<2>);
+
+  ops.def("rms_norm(Tensor! out, Tensor input, Tensor weight, float epsilon) -> ()");
+  ops.impl("rms_norm", torch::kCUDA, &rms_norm);
+  ops.def(
+      "fused_add_rms_norm(Tensor! input, Tensor! residual, Tensor weight, "
+      "float epsilon) -> ()");
+  ops.impl("fused_add_rms_norm", torch::kCUDA, &fused_add_rms_norm);
+
+  ops.def(
+      "rotary_embedding(Tensor positions, Tensor! query,"
+      "                 Tensor! key, int head_size,"
+      "                 Tensor cos_sin_cache, bool is_neox) -> ()");
+  ops.impl("rotary_embedding", torch::kCUDA, &rotary_embedding);
+  ops.def(
+      "batched_rotary_embedding(Tensor positions, Tensor! query,"
+      "                         Tensor! key, int head_size,"
+      "                         Tensor cos_sin_cache, bool is_neox,"
+      "                         int rot_dim,"
+      "                         Tensor cos_sin_cache_offsets) -> ()");
+  ops.impl("batched_rotary_embedding", torch::kCUDA, &batched_rotary_embedding);
+}
+
+TORCH_LIBRARY(_C_cache_ops, cache_ops) {
+  cache_ops.def("swap_blocks(Tensor src, Tensor! dst, Tensor block_mapping) -> ()");
+  cache_ops.impl("swap_blocks", torch::kCUDA, &swap_blocks);
+  cache_ops.def(
+      "copy_blocks(Tensor(a!)[] key_caches, Tensor[](b!) value_caches, "
+      "Tensor block_mapping) -> ()");
+  cache_ops.impl("copy_blocks", torch::kCUDA, &copy_blocks);
+  cache_ops.def(
+      "reshape_and_cache(Tensor key, Tensor value,"
+      "                  Tensor! key_cache, Tensor! value_cache,"
+      "                  Tensor slot_mapping,"
+      "                  str kv_cache_dtype,"
+      "                  float k_scale, float v_scale) -> ()");
+  cache_ops.impl("reshape_and_cache", torch::kCUDA, &reshape_and_cache);
+  cache_ops.def(
+      "reshape_and_cache_flash(Tensor key, Tensor value,"
+      "                        Tensor! key_cache,"
+      "                        Tensor! value_cache,"
+      "                        Tensor slot_mapping,"
+      "                        str kv_cache_dtype,"
+      "                        float k_scale, float v_scale) -> ()");
+  cache_ops.impl("reshape_and_cache_flash", torch::kCUDA, &reshape_and_cache_flash);
+  cache_ops.def(
+      "convert_fp8(Tensor! dst_cache, Tensor src_cache, float scale, "
+      "str kv_cache_dtype) -> ()");
+  cache_ops.impl("convert_fp8", torch::kCUDA, &convert_fp8);
+}
+
+TORCH_LIBRARY(_C_cuda_utils, cuda_utils) {
+  cuda_utils.def("get_device_attribute(int attribute, int device_id) -> int");
+  cuda_utils.impl("get_device_attribute", &get_device_attribute);
+  cuda_utils.def("get_max_shared_memory_per_block_device_attribute(int device_id) -> int");
+  cuda_utils.impl("get_max_shared_memory_per_block_device_attribute",
+                  &get_max_shared_memory_per_block_device_attribute);
+}
+
+// `import <pkg>._C` support (kernels/core/registration.h:22-27 of the reference does the same)
+PyMODINIT_FUNC PyInit__C() {
+  static struct PyModuleDef module = {PyModuleDef_HEAD_INIT, "_C", nullptr, 0, nullptr};
+  return PyModule_Create(&module);
+}

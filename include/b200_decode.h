@@ -1,0 +1,160 @@
+/*
+ * b200_decode.h — C ABI of libb200decode.so: the sm_100a decode hot path that drops in behind
+ * aphrodite-engine's custom-op boundary (aphrodite/_custom_ops.py -> torch.ops._C.* registered by
+ * kernels/torch_bindings.cpp in the reference).
+ *
+ * Every entry point takes plain device pointers, sizes/strides in ELEMENTS (as the reference
+ * launchers compute them from tensor strides) and a `cudaStream_t` passed as `void*`.
+ * No torch types cross this boundary; the torch-op shim (csrc/torch_shim.cpp) and the ctypes
+ * binding (aphrodite_engine_b200/_native.py) are both thin marshalling layers over it.
+ *
+ * Return value: 0 on success, non-zero on error (unsupported configuration, bad alignment, CUDA
+ * launch failure). b200_last_error() returns a thread-local, human-readable description — the
+ * shim turns it into the same RuntimeError the reference raises through TORCH_CHECK.
+ * All launches are asynchronous on `stream`, allocate nothing and never synchronise, so every op
+ * is CUDA-graph capturable (reference: decode runs under torch.cuda.graph,
+ * aphrodite/worker/model_runner.py:1682+).
+ *
+ * Each declaration cites the reference interface it replaces (path:line under the reference tree).
+ */
+#ifndef B200_DECODE_H_
+#define B200_DECODE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* activation / query dtype codes (torch scalar types Float / Half / BFloat16) */
+enum { B200_F32 = 0, B200_F16 = 1, B200_BF16 = 2 };
+/* kv-cache dtype codes: "auto" | "fp8"/"fp8_e4m3" | "fp8_e5m2"
+ * (kernels/quantization/fp8/nvidia/quant_utils.cuh:531-569 DISPATCH_BY_KV_CACHE_DTYPE) */
+enum { B200_KV_AUTO = 0, B200_KV_FP8_E4M3 = 1, B200_KV_FP8_E5M2 = 2 };
+
+const char* b200_last_error(void);
+/* library/ABI version, bumped when a signature changes */
+int b200_abi_version(void);
+/* parses the reference's kv_cache_dtype string; returns -1 for an unsupported string */
+int b200_parse_kv_cache_dtype(const char* s);
+
+/* ---- paged attention ------------------------------------------------------------------------
+ * replaces paged_attention_v1  kernels/attention/attention_kernels.cu:809-830 (schema
+ *          kernels/torch_bindings.cpp:25-35, prototype kernels/ops.h:6-16)
+ *          paged_attention_v2  kernels/attention/attention_kernels.cu:974-998 (schema :38-49)
+ * out        [num_seqs, num_heads, head_size]            (contiguous)
+ * query      [num_seqs, num_heads, head_size]            row stride q_stride (may be a qkv view)
+ * key_cache  [num_blocks, num_kv_heads, head_size/x, block_size, x]   x = 16 / sizeof(cache elt)
+ * value_cache[num_blocks, num_kv_heads, head_size, block_size]
+ * block_tables int32 [num_seqs, max_num_blocks_per_seq]; seq_lens int32 [num_seqs]
+ * alibi_slopes float32 [num_heads] or NULL
+ * v2 only: exp_sums,max_logits float32 [num_seqs,num_heads,max_num_partitions],
+ *          tmp_out [num_seqs,num_heads,max_num_partitions,head_size]; partition = 512 tokens
+ *          (aphrodite/attention/ops/paged_attn.py:13)
+ * blocksparse_* : vert_stride <= 1 disables block-sparse attention (attention_kernels.cu:773-789)
+ */
+int b200_paged_attention_v1(
+    void* out, const void* query, const void* key_cache, const void* value_cache,
+    int num_seqs, int num_heads, int num_kv_heads, int head_size, int block_size,
+    float scale, const int32_t* block_tables, const int32_t* seq_lens,
+    int max_num_blocks_per_seq, int max_seq_len, const float* alibi_slopes,
+    int64_t q_stride, int64_t kv_block_stride, int64_t kv_head_stride,
+    int dtype, int kv_dtype, float k_scale, float v_scale,
+    int tp_rank, int blocksparse_local_blocks, int blocksparse_vert_stride,
+    int blocksparse_block_size, int blocksparse_head_sliding_step, void* stream);
+
+int b200_paged_attention_v2(
+    void* out, float* exp_sums, float* max_logits, void* tmp_out,
+    const void* query, const void* key_cache, const void* value_cache,
+    int num_seqs, int num_heads, int num_kv_heads, int head_size, int block_size,
+    float scale, const int32_t* block_tables, const int32_t* seq_lens,
+    int max_num_blocks_per_seq, int max_seq_len, int max_num_partitions,
+    const float* alibi_slopes,
+    int64_t q_stride, int64_t kv_block_stride, int64_t kv_head_stride,
+    int dtype, int kv_dtype, float k_scale, float v_scale,
+    int tp_rank, int blocksparse_local_blocks, int blocksparse_vert_stride,
+    int blocksparse_block_size, int blocksparse_head_sliding_step, void* stream);
+
+/* Selects the implementation for the two calls above (debug / A-B measurement):
+ *   0 = auto (tensor-core bulk-copy kernel when the shape allows, generic SIMT kernel otherwise)
+ *   1 = force the generic SIMT kernel.  Returns the previous value. */
+int b200_set_attention_impl(int impl);
+/* 1 if the last paged_attention call on this thread took the tensor-core path, else 0 */
+int b200_last_attention_path(void);
+
+/* ---- cache ops ------------------------------------------------------------------------------
+ * replaces reshape_and_cache       kernels/cache_kernels.cu:263-289 (schema torch_bindings.cpp:467-473)
+ *          reshape_and_cache_flash kernels/cache_kernels.cu:304-330 (schema :476-484)
+ *          copy_blocks             kernels/cache_kernels.cu:101-148 (schema :461-464)
+ *          swap_blocks             kernels/cache_kernels.cu:24-63   (schema :456-458)
+ *          convert_fp8             kernels/cache_kernels.cu:356-410 (schema :487-490)
+ * slot_mapping int64 [num_tokens], negative = padding token (cache_kernels.cu:166)
+ */
+int b200_reshape_and_cache(
+    const void* key, const void* value, void* key_cache, void* value_cache,
+    const int64_t* slot_mapping, int num_tokens, int num_heads, int head_size,
+    int block_size, int x, int64_t key_stride, int64_t value_stride,
+    int dtype, int kv_dtype, float k_scale, float v_scale, void* stream);
+
+int b200_reshape_and_cache_flash(
+    const void* key, const void* value, void* key_cache, void* value_cache,
+    const int64_t* slot_mapping, int num_tokens, int num_heads, int head_size,
+    int block_size, int64_t block_stride, int64_t key_stride, int64_t value_stride,
+    int dtype, int kv_dtype, float k_scale, float v_scale, void* stream);
+
+/* key_cache_ptrs / value_cache_ptrs: DEVICE arrays of num_layers device pointers;
+ * block_mapping: DEVICE int64 [num_pairs, 2] (src, dst); block_bytes = bytes of one block of one
+ * layer's key (== value) cache. Byte-exact copy. */
+int b200_copy_blocks(
+    const int64_t* key_cache_ptrs, const int64_t* value_cache_ptrs,
+    const int64_t* block_mapping, int num_layers, int num_pairs,
+    int64_t block_bytes, void* stream);
+
+/* block_mapping: HOST int64 [num_pairs, 2]; kind: 0 = D2D, 1 = D2H, 2 = H2D
+ * (one cudaMemcpyAsync per pair, as the reference: cache_kernels.cu:55-62) */
+int b200_swap_blocks(
+    const void* src, void* dst, const int64_t* block_mapping_host, int num_pairs,
+    int64_t block_bytes, int kind, void* stream);
+
+/* src_dtype/dst_dtype: B200_F32/F16/BF16 or -1 for the uint8 fp8 side; exactly one side is fp8.
+ * kv_dtype "auto" means e4m3, as in the reference (cache_kernels.cu:375-389). */
+int b200_convert_fp8(
+    void* dst, const void* src, int64_t numel, int src_dtype, int dst_dtype,
+    int kv_dtype, float scale, void* stream);
+
+/* ---- normalisation / rotary / activation ------------------------------------------------------
+ * replaces rms_norm            kernels/layernorm_kernels.cu:290-307 (schema torch_bindings.cpp:97-100)
+ *          fused_add_rms_norm  kernels/layernorm_kernels.cu:319-352 (schema :103-106)
+ *          rotary_embedding    kernels/pos_encoding_kernels.cu:128-165 (schema :110-114)
+ *          batched_rotary_embedding  kernels/pos_encoding_kernels.cu:171-206 (schema :118-124)
+ *          silu_and_mul / gelu_and_mul / gelu_tanh_and_mul  kernels/activation_kernels.cu:66-82
+ *          gelu_new / gelu_fast / gelu_quick                kernels/activation_kernels.cu:143-160
+ */
+int b200_rms_norm(void* out, const void* input, const void* weight, float epsilon,
+                  int num_tokens, int hidden_size, int dtype, void* stream);
+int b200_fused_add_rms_norm(void* input, void* residual, const void* weight, float epsilon,
+                            int num_tokens, int hidden_size, int dtype, void* stream);
+/* cos_sin_cache [max_position, rot_dim]; positions int64 [num_tokens];
+ * cos_sin_cache_offsets int64 [num_tokens] or NULL (plain rotary_embedding) */
+int b200_rotary_embedding(const int64_t* positions, void* query, void* key,
+                          const void* cos_sin_cache, const int64_t* cos_sin_cache_offsets,
+                          int num_tokens, int num_heads, int num_kv_heads, int head_size,
+                          int rot_dim, int64_t query_stride, int64_t key_stride,
+                          int is_neox, int dtype, void* stream);
+/* act: 0 silu_and_mul, 1 gelu_and_mul, 2 gelu_tanh_and_mul  (input [T, 2d] -> out [T, d]) */
+int b200_act_and_mul(void* out, const void* input, int num_tokens, int d, int act,
+                     int dtype, void* stream);
+/* act: 0 gelu_new, 1 gelu_fast, 2 gelu_quick (input [T, d] -> out [T, d]) */
+int b200_activation(void* out, const void* input, int num_tokens, int d, int act,
+                    int dtype, void* stream);
+
+/* ---- device queries -----------------------------------------------------------------------------
+ * replaces get_device_attribute / get_max_shared_memory_per_block_device_attribute
+ *          kernels/cuda_utils_kernels.cu (schema torch_bindings.cpp:497-504) */
+int64_t b200_get_device_attribute(int64_t attribute, int64_t device_id);
+int64_t b200_get_max_shared_memory_per_block_device_attribute(int64_t device_id);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_DECODE_H_ */

@@ -1,0 +1,230 @@
+"""GPU parity: paged_attention_v1 / v2 (CUDA path through torch.ops._C.* -> C ABI) vs the CPU oracle.
+Mirrors the reference's tests/kernels/test_attention.py parametrisation (heads, head sizes, block
+sizes, dtypes, kv dtypes, ALiBi) plus ragged / edge-case sequence lengths and the block-sparse path."""
+import random
+
+import pytest
+import torch
+
+from oracle import paged_ops as po
+from tests import tolerances as tol
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _mk(num_seqs, num_heads, num_kv_heads, head_size, block_size, dtype, kv_dtype, seq_lens,
+        seed=0, use_alibi=False, num_blocks=None):
+    torch.manual_seed(seed)
+    random.seed(seed)
+    max_len = max(max(seq_lens), 1)
+    max_blocks = (max_len + block_size - 1) // block_size
+    if num_blocks is None:
+        num_blocks = max(num_seqs * max_blocks, 8)
+    scale = head_size ** -0.5
+    q = torch.empty(num_seqs, num_heads, head_size).uniform_(-scale, scale).to(dtype)
+    kc, vc = po.make_kv_cache(num_blocks, block_size, num_kv_heads, head_size, dtype, kv_dtype, seed)
+    perm = torch.randperm(num_blocks)[: num_seqs * max_blocks] if num_blocks >= num_seqs * max_blocks \
+        else torch.randint(0, num_blocks, (num_seqs * max_blocks,))
+    bt = perm.view(num_seqs, max_blocks).to(torch.int32)
+    sl = torch.tensor(seq_lens, dtype=torch.int32)
+    alibi = torch.randn(num_heads, dtype=torch.float32) if use_alibi else None
+    return q, kc, vc, bt, sl, alibi, scale
+
+
+def _run(ops, version, q, kc, vc, bt, sl, alibi, scale, num_kv_heads, block_size, kv_dtype,
+         k_scale=1.0, v_scale=1.0, **bs):
+    qd, kcd, vcd, btd, sld = (t.to(DEV) for t in (q, kc, vc, bt, sl))
+    ad = alibi.to(DEV) if alibi is not None else None
+    out = torch.full_like(qd, float("nan"))
+    max_len = int(sl.max())
+    if version == "v1":
+        ops.paged_attention_v1(out, qd, kcd, vcd, num_kv_heads, scale, btd, sld, block_size,
+                               max_len, ad, kv_dtype, k_scale, v_scale, **bs)
+    else:
+        S, H, D = q.shape
+        P = (max_len + 511) // 512
+        tmp = torch.full((S, H, P, D), float("nan"), dtype=q.dtype, device=DEV)
+        es = torch.full((S, H, P), float("nan"), dtype=torch.float32, device=DEV)
+        ml = torch.full((S, H, P), float("nan"), dtype=torch.float32, device=DEV)
+        ops.paged_attention_v2(out, es, ml, tmp, qd, kcd, vcd, num_kv_heads, scale, btd, sld,
+                               block_size, max_len, ad, kv_dtype, k_scale, v_scale, **bs)
+    torch.cuda.synchronize()
+    return out.cpu()
+
+
+def _check(out, ref, kv_dtype):
+    atol = tol.ATTN_FP8_ATOL if kv_dtype != "auto" else tol.ATTN_ATOL
+    assert torch.isfinite(out.float()).all()
+    torch.testing.assert_close(out.float(), ref.float(), atol=atol, rtol=tol.ATTN_RTOL)
+
+
+@pytest.mark.parametrize("version", ["v1", "v2"])
+@pytest.mark.parametrize("heads", [(40, 40), (64, 8), (32, 8)])
+@pytest.mark.parametrize("head_size", [64, 80, 96, 112, 128, 192, 256])
+@pytest.mark.parametrize("block_size", [16, 32])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_tensor_core_path(ops, cabi, version, heads, head_size, block_size, dtype):
+    nh, nkv = heads
+    seq_lens = [1, 15, 16, 17, 513, 1025, 700]
+    q, kc, vc, bt, sl, alibi, scale = _mk(len(seq_lens), nh, nkv, head_size, block_size, dtype,
+                                          "auto", seq_lens)
+    out = _run(ops, version, q, kc, vc, bt, sl, None, scale, nkv, block_size, "auto")
+    assert cabi.b200_last_attention_path() == 1, "expected the tensor-core kernel"
+    _check(out, po.paged_attention(q, kc, vc, bt, sl, scale), "auto")
+
+
+@pytest.mark.parametrize("version", ["v1", "v2"])
+@pytest.mark.parametrize("kv_dtype", ["fp8", "fp8_e5m2"])
+@pytest.mark.parametrize("head_size", [64, 128, 256])
+@pytest.mark.parametrize("block_size", [16, 32])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_fp8_kv(ops, cabi, version, kv_dtype, head_size, block_size, dtype):
+    seq_lens = [3, 33, 640, 1100]
+    q, kc, vc, bt, sl, _, scale = _mk(len(seq_lens), 16, 4, head_size, block_size, dtype, kv_dtype,
+                                      seq_lens)
+    for ks, vs in ((1.0, 1.0), (0.75, 1.5)):
+        out = _run(ops, version, q, kc, vc, bt, sl, None, scale, 4, block_size, kv_dtype, ks, vs)
+        assert cabi.b200_last_attention_path() == 1
+        ref = po.paged_attention(q, kc, vc, bt, sl, scale, None, kv_dtype, ks, vs)
+        _check(out, ref, kv_dtype)
+
+
+@pytest.mark.parametrize("version", ["v1", "v2"])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32])
+def test_alibi(ops, version, dtype):
+    seq_lens = [7, 129, 900]
+    q, kc, vc, bt, sl, alibi, scale = _mk(3, 16, 4, 128, 16, dtype, "auto", seq_lens,
+                                          use_alibi=True)
+    out = _run(ops, version, q, kc, vc, bt, sl, alibi, scale, 4, 16, "auto")
+    _check(out, po.paged_attention(q, kc, vc, bt, sl, scale, alibi), "auto")
+
+
+@pytest.mark.parametrize("version", ["v1", "v2"])
+@pytest.mark.parametrize("cfg", [
+    # (dtype, head_size, block_size, kv_dtype): shapes only the generic SIMT kernel covers
+    (torch.float32, 128, 16, "auto"), (torch.float32, 64, 8, "auto"), (torch.float32, 256, 32, "auto"),
+    (torch.bfloat16, 120, 16, "auto"), (torch.float16, 120, 32, "auto"),
+    (torch.bfloat16, 128, 8, "auto"), (torch.float16, 80, 8, "auto"),
+    (torch.bfloat16, 128, 8, "fp8"), (torch.float32, 128, 16, "fp8"),
+])
+def test_generic_path(ops, cabi, version, cfg):
+    dtype, head_size, block_size, kv_dtype = cfg
+    seq_lens = [1, 9, 300, 1030]
+    q, kc, vc, bt, sl, _, scale = _mk(4, 8, 2, head_size, block_size, dtype, kv_dtype, seq_lens)
+    out = _run(ops, version, q, kc, vc, bt, sl, None, scale, 2, block_size, kv_dtype)
+    assert cabi.b200_last_attention_path() == 0
+    _check(out, po.paged_attention(q, kc, vc, bt, sl, scale, None, kv_dtype), kv_dtype)
+
+
+@pytest.mark.parametrize("version", ["v1", "v2"])
+def test_forced_generic_matches_tensor_core(ops, cabi, version):
+    seq_lens = [5, 250, 1500]
+    q, kc, vc, bt, sl, _, scale = _mk(3, 32, 8, 128, 16, torch.bfloat16, "auto", seq_lens)
+    a = _run(ops, version, q, kc, vc, bt, sl, None, scale, 8, 16, "auto")
+    prev = cabi.b200_set_attention_impl(1)
+    try:
+        b = _run(ops, version, q, kc, vc, bt, sl, None, scale, 8, 16, "auto")
+        assert cabi.b200_last_attention_path() == 0
+    finally:
+        cabi.b200_set_attention_impl(prev)
+    _check(a, b, "auto")
+
+
+@pytest.mark.parametrize("version", ["v1", "v2"])
+@pytest.mark.parametrize("sliding", [0, 2, -1])
+def test_blocksparse(ops, version, sliding):
+    seq_lens = [64, 777, 2000]
+    q, kc, vc, bt, sl, _, scale = _mk(3, 8, 2, 128, 16, torch.bfloat16, "auto", seq_lens)
+    bs = dict(tp_rank=1, blocksparse_local_blocks=4, blocksparse_vert_stride=3,
+              blocksparse_block_size=64, blocksparse_head_sliding_step=sliding)
+    out = _run(ops, version, q, kc, vc, bt, sl, None, scale, 2, 16, "auto", **bs)
+    ref = po.paged_attention(q, kc, vc, bt, sl, scale, None, "auto", 1.0, 1.0, **bs)
+    _check(out, ref, "auto")
+
+
+def test_strided_query_and_padding_rows(ops):
+    """q is a view into a fused qkv tensor (q_stride != H*D) — reference attention_kernels.cu:705."""
+    S, H, KV, D, BS = 6, 32, 8, 128, 16
+    seq_lens = [40, 1, 16, 333, 512, 513]
+    q, kc, vc, bt, sl, _, scale = _mk(S, H, KV, D, BS, torch.bfloat16, "auto", seq_lens)
+    qkv = torch.zeros(S, (H + 2 * KV) * D, dtype=torch.bfloat16, device=DEV)
+    qkv[:, : H * D] = q.view(S, -1).to(DEV)
+    qv = qkv[:, : H * D].view(S, H, D)
+    out = torch.empty(S, H, D, dtype=torch.bfloat16, device=DEV)
+    ops.paged_attention_v1(out, qv, kc.to(DEV), vc.to(DEV), KV, scale, bt.to(DEV), sl.to(DEV), BS,
+                           max(seq_lens), None, "auto", 1.0, 1.0)
+    _check(out.cpu(), po.paged_attention(q, kc, vc, bt, sl, scale), "auto")
+
+
+def test_zero_length_sequence_writes_zeros(ops):
+    q, kc, vc, bt, sl, _, scale = _mk(2, 8, 2, 128, 16, torch.bfloat16, "auto", [0, 20])
+    out = _run(ops, "v1", q, kc, vc, bt, sl, None, scale, 2, 16, "auto")
+    assert (out[0] == 0).all()
+    _check(out[1:], po.paged_attention(q, kc, vc, bt, sl, scale)[1:], "auto")
+
+
+def test_nan_in_unused_slots_is_ignored(ops):
+    """Tokens past seq_len in the last block may hold NaNs (reference zeroes V there, :412-421)."""
+    q, kc, vc, bt, sl, _, scale = _mk(2, 8, 2, 128, 16, torch.bfloat16, "auto", [5, 21])
+    ref = po.paged_attention(q, kc, vc, bt, sl, scale)
+    for s, n in enumerate([5, 21]):
+        blk = int(bt[s, n // 16])
+        kc[blk, :, :, n % 16:, :] = float("nan")
+        vc[blk, :, :, n % 16:] = float("nan")
+    out = _run(ops, "v1", q, kc, vc, bt, sl, None, scale, 2, 16, "auto")
+    _check(out, ref, "auto")
+
+
+def test_unsupported_shapes_raise(ops):
+    q, kc, vc, bt, sl, _, scale = _mk(1, 8, 2, 128, 16, torch.bfloat16, "auto", [5])
+    out = torch.empty_like(q, device=DEV)
+    with pytest.raises(RuntimeError, match="Unsupported block size"):
+        ops.paged_attention_v1(out, q.to(DEV), kc.to(DEV), vc.to(DEV), 2, scale, bt.to(DEV),
+                               sl.to(DEV), 4, 5, None, "auto", 1.0, 1.0)
+    with pytest.raises(RuntimeError, match="Unsupported data type of kv cache"):
+        ops.paged_attention_v1(out, q.to(DEV), kc.to(DEV), vc.to(DEV), 2, scale, bt.to(DEV),
+                               sl.to(DEV), 16, 5, None, "int8", 1.0, 1.0)
+    q2 = torch.zeros(1, 8, 72, dtype=torch.bfloat16, device=DEV)
+    with pytest.raises(RuntimeError, match="Unsupported head size"):
+        ops.paged_attention_v1(torch.empty_like(q2), q2, kc.to(DEV), vc.to(DEV), 2, scale,
+                               bt.to(DEV), sl.to(DEV), 16, 5, None, "auto", 1.0, 1.0)
+
+
+def test_full_size_properties(ops):
+    """BASELINE config 2 shape per layer (bs 256, ctx 4096, 32q/8kv/128, block 16) is too big for the
+    CPU oracle in seconds; check size-independent properties instead:
+      * GQA consistency: duplicating a q-head gives identical rows,
+      * v1 == v2 (partitioned) within tolerance,
+      * a sub-sample of sequences equals the oracle."""
+    S, H, KV, D, BS, CTX = 256, 32, 8, 128, 16, 4096
+    nb_per = CTX // BS
+    g = torch.Generator(device=DEV).manual_seed(0)
+    scale = D ** -0.5
+    kv = torch.empty(2, S * nb_per, BS * KV * D, dtype=torch.bfloat16, device=DEV)
+    kv.uniform_(-scale, scale, generator=g)
+    kc = kv[0].view(S * nb_per, KV, D // 8, BS, 8)
+    vc = kv[1].view(S * nb_per, KV, D, BS)
+    q = torch.empty(S, H, D, dtype=torch.bfloat16, device=DEV).uniform_(-scale, scale, generator=g)
+    q[:, 1] = q[:, 0]
+    bt = torch.randperm(S * nb_per, device=DEV, generator=g).view(S, nb_per).to(torch.int32)
+    sl = torch.full((S,), CTX, dtype=torch.int32, device=DEV)
+    sl[::7] = torch.randint(1, CTX, (len(sl[::7]),), device=DEV, generator=g).to(torch.int32)
+    o1 = torch.empty_like(q)
+    ops.paged_attention_v1(o1, q, kc, vc, KV, scale, bt, sl, BS, CTX, None, "auto", 1.0, 1.0)
+    P = CTX // 512
+    o2 = torch.empty_like(q)
+    tmp = torch.empty(S, H, P, D, dtype=q.dtype, device=DEV)
+    es = torch.empty(S, H, P, dtype=torch.float32, device=DEV)
+    ml = torch.empty_like(es)
+    ops.paged_attention_v2(o2, es, ml, tmp, q, kc, vc, KV, scale, bt, sl, BS, CTX, None, "auto",
+                           1.0, 1.0)
+    torch.cuda.synchronize()
+    assert torch.equal(o1[:, 0], o1[:, 1])
+    torch.testing.assert_close(o1.float(), o2.float(), atol=tol.ATTN_ATOL, rtol=tol.ATTN_RTOL)
+    pick = [0, 7, 100, 255]
+    blocks = bt[pick].flatten().long()            # distinct blocks (block table is a permutation)
+    bt_small = torch.arange(len(blocks), dtype=torch.int32).view(len(pick), nb_per)
+    ref = po.paged_attention(q[pick].cpu(), kc[blocks].cpu(), vc[blocks].cpu(), bt_small,
+                             sl[pick].cpu(), scale)
+    _check(o1[pick].cpu(), ref, "auto")
