@@ -66,7 +66,13 @@ struct FastCfg {
   static constexpr int STAGE = 2 * CHUNK;
   static constexpr int RING_BUDGET = 100 * 1024;
   static constexpr int NSTAGES_RAW = RING_BUDGET / STAGE;
-  static constexpr int NSTAGES = NSTAGES_RAW > 16 ? 16 : (NSTAGES_RAW < 2 ? 2 : NSTAGES_RAW);
+  // The stage count MUST be a multiple of the consumer-warp count: stage s is then always consumed
+  // by warp s % kConsumerWarps, so the parity waits on one mbarrier are issued in program order by a
+  // single warp. (With e.g. 6 stages / 4 warps a fast warp could test parity 1 of a barrier whose
+  // phase 0 is still in flight — that test passes vacuously and the warp would read a stale stage.)
+  static constexpr int NSTAGES_CAP = NSTAGES_RAW > 16 ? 16 : NSTAGES_RAW;
+  static constexpr int NSTAGES =
+      NSTAGES_CAP < kConsumerWarps ? kConsumerWarps : (NSTAGES_CAP / kConsumerWarps) * kConsumerWarps;
   static constexpr int OPAD = D + 4;  // merge buffer row pitch (floats)
   static constexpr int MERGE_BYTES = kConsumerWarps * kHeadsPerCta * OPAD * 4;
   static constexpr int RING_BYTES = NSTAGES * STAGE;

@@ -20,7 +20,7 @@ def _name(dt):
 def test_rms_norm(ops, dtype, shape, fused):
     T, Hd = shape
     torch.manual_seed(0)
-    x = (torch.randn(T, Hd) * (1.0 / (2 * Hd) ** 0.5 if False else 1.0)).to(dtype)
+    x = torch.randn(T, Hd).to(dtype)
     r = torch.randn(T, Hd).to(dtype)
     w = torch.empty(Hd).normal_(1.0, 0.1).to(dtype)
     eps = 1e-6
@@ -38,9 +38,10 @@ def test_rms_norm(ops, dtype, shape, fused):
         torch.cuda.synchronize()
         got = out.cpu()
     torch.testing.assert_close(got.float(), ref_x.float(), atol=tol.NORM_ATOL, rtol=tol.NORM_RTOL)
-    # and much tighter than the reference's own bound: at most 1 ulp of the output dtype
+    # and much tighter than the reference's own bound: two roundings (T(x*s), then *w) whose first
+    # one may flip by an ulp when the fp32 reduction order differs -> at most ~2 ulp of the output
     ulp = {torch.bfloat16: 2 ** -7, torch.float16: 2 ** -10, torch.float32: 1e-5}[dtype]
-    assert ((got.float() - ref_x.float()).abs() <= ulp * ref_x.float().abs() + 1e-6).all()
+    assert ((got.float() - ref_x.float()).abs() <= 2.5 * ulp * ref_x.float().abs() + 1e-6).all()
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
