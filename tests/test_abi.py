@@ -1,0 +1,148 @@
+"""CPU-only: the C-ABI library loads without a GPU and exports every symbol include/*.h declares;
+the torch-op shim registers the reference's schemas (kernels/torch_bindings.cpp) verbatim; the
+product package never imports the oracle. No compute calls here."""
+import ctypes
+import glob
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    syms = set()
+    for h in glob.glob(os.path.join(ROOT, "include", "*.h")):
+        txt = re.sub(r"/\*.*?\*/", "", open(h).read(), flags=re.S)
+        syms |= set(re.findall(r"\b(b200_\w+)\s*\(", txt))
+    return syms
+
+
+def test_header_symbols_are_exported_and_bound():
+    from aphrodite_engine_b200 import _native
+    lib = _native.load_c_abi()
+    declared = _declared_symbols()
+    assert len(declared) >= 19
+    for s in declared:
+        assert hasattr(lib, s), f"{s} declared in include/ but not exported by libb200decode.so"
+    assert declared == set(_native.SIGNATURES), "ctypes table and header disagree"
+    assert lib.b200_abi_version() == 1
+    assert lib.b200_parse_kv_cache_dtype(b"auto") == 0
+    assert lib.b200_parse_kv_cache_dtype(b"fp8") == 1 == lib.b200_parse_kv_cache_dtype(b"fp8_e4m3")
+    assert lib.b200_parse_kv_cache_dtype(b"fp8_e5m2") == 2
+    assert lib.b200_parse_kv_cache_dtype(b"int8") == -1
+
+
+def test_library_is_sm100a_only_and_has_no_torch_dependency():
+    from aphrodite_engine_b200 import _native
+    out = subprocess.run(["ldd", _native.LIB_PATH], capture_output=True, text=True).stdout
+    assert "libtorch" not in out and "libc10" not in out
+    cuobjdump = "/usr/local/cuda/bin/cuobjdump"
+    if os.path.exists(cuobjdump):
+        arch = subprocess.run([cuobjdump, "-lelf", _native.LIB_PATH], capture_output=True, text=True).stdout
+        assert "sm_100a" in arch
+        assert not re.search(r"sm_(?!100a)\d+", arch), arch
+
+
+# Schema strings copied from the reference's registration file (kernels/torch_bindings.cpp:25-124,
+# :456-504): the drop-in must register byte-for-byte equivalent signatures (names, types, `!` marks).
+REF_SCHEMAS = {
+    "_C::paged_attention_v1":
+        "paged_attention_v1(Tensor! out, Tensor query, Tensor key_cache, Tensor value_cache, int num_kv_heads,"
+        " float scale, Tensor block_tables, Tensor seq_lens, int block_size, int max_seq_len,"
+        " Tensor? alibi_slopes, str kv_cache_dtype, float k_scale, float v_scale, int tp_rank,"
+        " int blocksparse_local_blocks, int blocksparse_vert_stride, int blocksparse_block_size,"
+        " int blocksparse_head_sliding_step) -> ()",
+    "_C::paged_attention_v2":
+        "paged_attention_v2(Tensor! out, Tensor! exp_sums, Tensor! max_logits, Tensor! tmp_out, Tensor query,"
+        " Tensor key_cache, Tensor value_cache, int num_kv_heads, float scale, Tensor block_tables,"
+        " Tensor seq_lens, int block_size, int max_seq_len, Tensor? alibi_slopes, str kv_cache_dtype,"
+        " float k_scale, float v_scale, int tp_rank, int blocksparse_local_blocks,"
+        " int blocksparse_vert_stride, int blocksparse_block_size, int blocksparse_head_sliding_step) -> ()",
+    "_C::silu_and_mul": "silu_and_mul(Tensor! out, Tensor input) -> ()",
+    "_C::gelu_and_mul": "gelu_and_mul(Tensor! out, Tensor input) -> ()",
+    "_C::gelu_tanh_and_mul": "gelu_tanh_and_mul(Tensor! out, Tensor input) -> ()",
+    "_C::gelu_new": "gelu_new(Tensor! out, Tensor input) -> ()",
+    "_C::gelu_fast": "gelu_fast(Tensor! out, Tensor input) -> ()",
+    "_C::gelu_quick": "gelu_quick(Tensor! out, Tensor input) -> ()",
+    "_C::rms_norm": "rms_norm(Tensor! out, Tensor input, Tensor weight, float epsilon) -> ()",
+    "_C::fused_add_rms_norm":
+        "fused_add_rms_norm(Tensor! input, Tensor! residual, Tensor weight, float epsilon) -> ()",
+    "_C::rotary_embedding":
+        "rotary_embedding(Tensor positions, Tensor! query, Tensor! key, int head_size, Tensor cos_sin_cache,"
+        " bool is_neox) -> ()",
+    "_C::batched_rotary_embedding":
+        "batched_rotary_embedding(Tensor positions, Tensor! query, Tensor! key, int head_size,"
+        " Tensor cos_sin_cache, bool is_neox, int rot_dim, Tensor cos_sin_cache_offsets) -> ()",
+    "_C_cache_ops::swap_blocks": "swap_blocks(Tensor src, Tensor! dst, Tensor block_mapping) -> ()",
+    "_C_cache_ops::copy_blocks":
+        "copy_blocks(Tensor(a!)[] key_caches, Tensor[](b!) value_caches, Tensor block_mapping) -> ()",
+    "_C_cache_ops::reshape_and_cache":
+        "reshape_and_cache(Tensor key, Tensor value, Tensor! key_cache, Tensor! value_cache,"
+        " Tensor slot_mapping, str kv_cache_dtype, float k_scale, float v_scale) -> ()",
+    "_C_cache_ops::reshape_and_cache_flash":
+        "reshape_and_cache_flash(Tensor key, Tensor value, Tensor! key_cache, Tensor! value_cache,"
+        " Tensor slot_mapping, str kv_cache_dtype, float k_scale, float v_scale) -> ()",
+    "_C_cache_ops::convert_fp8":
+        "convert_fp8(Tensor! dst_cache, Tensor src_cache, float scale, str kv_cache_dtype) -> ()",
+    "_C_cuda_utils::get_device_attribute": "get_device_attribute(int attribute, int device_id) -> int",
+    "_C_cuda_utils::get_max_shared_memory_per_block_device_attribute":
+        "get_max_shared_memory_per_block_device_attribute(int device_id) -> int",
+}
+
+
+def _sig(schema):
+    return ([(a.name, str(a.type), bool(a.alias_info and a.alias_info.is_write)) for a in schema.arguments],
+            [str(r.type) for r in schema.returns])
+
+
+@pytest.mark.parametrize("op", sorted(REF_SCHEMAS))
+def test_torch_ops_registered_with_reference_schema(op):
+    from aphrodite_engine_b200 import _native
+    _native.load_torch_ops()
+    ns, name = op.split("::")
+    packet = getattr(getattr(torch.ops, ns), name)
+    ours = packet.default._schema
+    ref = torch._C.parse_schema(f"{ns}::{REF_SCHEMAS[op]}")
+    assert _sig(ours) == _sig(ref), f"{op}: {ours} != {ref}"
+
+
+def test_shim_exports_pyinit_for_import_as_aphrodite_C():
+    from aphrodite_engine_b200 import _native
+    lib = ctypes.CDLL(_native.SHIM_PATH)
+    assert hasattr(lib, "PyInit__C")
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "aphrodite_engine_b200")
+    offenders = []
+    for dirpath, _, files in os.walk(pkg):
+        if "build" in dirpath.split(os.sep):
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                if re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M) or "oracle/" in txt and f.endswith(".py") \
+                        and re.search(r"(open|load|CDLL)\(.*oracle", txt):
+                    offenders.append(f)
+    assert not offenders, offenders
+
+
+def test_missing_extension_fails_loudly(tmp_path, monkeypatch):
+    from aphrodite_engine_b200 import _native
+    monkeypatch.setattr(_native, "_lib", None)
+    monkeypatch.setattr(_native, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(ImportError, match="no CPU/PyTorch fallback"):
+        _native.load_c_abi()
+
+
+def test_ops_refuse_cpu_tensors():
+    """There is no CPU dispatch key registered: a CPU call must raise, not silently compute."""
+    import aphrodite_engine_b200._custom_ops as ops
+    x = torch.randn(2, 8)
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        ops.silu_and_mul(torch.empty(2, 4), x)
