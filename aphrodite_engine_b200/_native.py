@@ -13,6 +13,8 @@ import torch
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libb200decode.so")
 SHIM_PATH = os.path.join(_PKG, "_C.abi3.so")
+CORE_PATH = os.path.join(_PKG, "_core_C.abi3.so")
+MOE_PATH = os.path.join(_PKG, "_moe_C.abi3.so")
 
 _lib = None
 _ops_loaded = False
@@ -44,6 +46,12 @@ SIGNATURES = {
     "b200_rotary_embedding": [c_void_p] * 5 + [c_int] * 5 + [c_int64] * 2 + [c_int] * 2 + [c_void_p],
     "b200_act_and_mul": [c_void_p] * 2 + [c_int] * 4 + [c_void_p],
     "b200_activation": [c_void_p] * 2 + [c_int] * 4 + [c_void_p],
+    "b200_marlin_gemm_plan": [c_int] * 4,
+    "b200_gptq_marlin_gemm": [c_void_p] * 6 + [c_int] * 8 + [c_void_p],
+    "b200_gptq_marlin_repack": [c_void_p] * 3 + [c_int] * 3 + [c_void_p],
+    "b200_awq_marlin_repack": [c_void_p] * 2 + [c_int] * 3 + [c_void_p],
+    "b200_moe_align_block_size": [c_void_p, c_int, c_int64, c_int, c_int] + [c_void_p] * 4,
+    "b200_topk_softmax": [c_void_p] * 4 + [c_int] * 3 + [c_void_p],
     "b200_get_device_attribute": [c_int64, c_int64],
     "b200_get_max_shared_memory_per_block_device_attribute": [c_int64],
 }
@@ -86,9 +94,26 @@ def load_torch_ops():
         if not os.path.exists(SHIM_PATH):
             raise _missing(SHIM_PATH)
         load_c_abi()
+        load_core_ext()
         torch.ops.load_library(SHIM_PATH)
+        if not os.path.exists(MOE_PATH):
+            raise _missing(MOE_PATH)
+        torch.ops.load_library(MOE_PATH)
         _ops_loaded = True
     return torch.ops._C
+
+
+def load_core_ext():
+    """Makes `torch.classes._core_C.ScalarType` available (the `b_q_type` argument type of the marlin op).
+    If the reference's own `_core_C` extension already registered the class, it is used as is."""
+    try:
+        return torch.classes._core_C.ScalarType
+    except Exception:
+        pass
+    if not os.path.exists(CORE_PATH):
+        raise _missing(CORE_PATH)
+    torch.ops.load_library(CORE_PATH)
+    return torch.classes._core_C.ScalarType
 
 
 def last_error() -> str:

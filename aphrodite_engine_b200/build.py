@@ -19,8 +19,11 @@ CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(PKG, "build", "obj")
 LIB = os.path.join(PKG, "libb200decode.so")
 SHIM = os.path.join(PKG, "_C.abi3.so")
+CORE = os.path.join(PKG, "_core_C.abi3.so")
+MOE = os.path.join(PKG, "_moe_C.abi3.so")
 
-CU_SOURCES = ["runtime.cu", "paged_attention.cu", "cache_ops.cu", "norm_rope_act.cu"]
+CU_SOURCES = ["runtime.cu", "paged_attention.cu", "cache_ops.cu", "norm_rope_act.cu", "marlin_repack.cu",
+              "marlin_gemm.cu", "moe_ops.cu"]
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(ROOT, "include", "b200_decode.h")]
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -68,10 +71,11 @@ def build_lib(verbose=False):
     return LIB
 
 
-def build_shim(verbose=False):
+def build_shim(verbose=False, name="_C"):
     import torch
 
-    src = os.path.join(CSRC, "torch_shim.cpp")
+    src = os.path.join(CSRC, "torch_shim.cpp" if name == "_C" else "moe_shim.cpp")
+    SHIM = os.path.join(PKG, f"{name}.abi3.so")
     if not _stale(SHIM, [src, LIB] + HEADERS):
         return SHIM
     tdir = os.path.dirname(torch.__file__)
@@ -85,15 +89,37 @@ def build_shim(verbose=False):
         "-lc10", "-lc10_cuda", "-ltorch_python", "-L/usr/local/cuda/lib64", "-lcudart",
         "-Wl,-rpath,$ORIGIN", f"-Wl,-rpath,{tdir}/lib",
     ]
-    _run(cmd, os.path.join(OBJ, "torch_shim.log"))
+    _run(cmd, os.path.join(OBJ, f"shim{name}.log"))
     if verbose:
         print("built", SHIM)
     return SHIM
 
 
+def build_core(verbose=False):
+    """`_core_C.abi3.so`: this repo's own ScalarType custom class (csrc/core_scalar_type.cpp)."""
+    import torch
+
+    src = os.path.join(CSRC, "core_scalar_type.cpp")
+    if not _stale(CORE, [src]):
+        return CORE
+    tdir = os.path.dirname(torch.__file__)
+    abi = int(torch._C._GLIBCXX_USE_CXX11_ABI)
+    os.makedirs(OBJ, exist_ok=True)
+    _run(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-w", f"-D_GLIBCXX_USE_CXX11_ABI={abi}",
+          f"-I{tdir}/include", f"-I{tdir}/include/torch/csrc/api/include",
+          f"-I{sysconfig.get_paths()['include']}", src, "-o", CORE, f"-L{tdir}/lib", "-ltorch",
+          "-ltorch_cpu", "-lc10", "-ltorch_python", f"-Wl,-rpath,{tdir}/lib"],
+         os.path.join(OBJ, "core_scalar_type.log"))
+    if verbose:
+        print("built", CORE)
+    return CORE
+
+
 def build(verbose=False):
     build_lib(verbose)
-    build_shim(verbose)
+    build_core(verbose)
+    build_shim(verbose, "_C")
+    build_shim(verbose, "_moe_C")
 
 
 if __name__ == "__main__":

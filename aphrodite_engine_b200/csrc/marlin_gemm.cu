@@ -1,0 +1,483 @@
+// marlin_gemm.cu — W4A16 GEMM in the Marlin weight format on 5th-gen tensor cores (tcgen05 + TMEM), sm_100a.
+//
+// Replaces gptq_marlin_gemm (kernels/quantization/gptq_marlin/gptq_marlin.cu:2247-2430 entry, :527-1764
+// kernel) for the 4-bit GPTQ (uint4b8) and AWQ (uint4 + integer zero points) formats:
+//     C[M,N] = A[M,K] . W,   W[k,n] = (q[k,n] - 8 | zp[g,n]) * s[g,n]     (fp32 accumulate)
+// Not a port: the reference is an Ampere design (cp.async + ldmatrix + mma.sync.m16n8k16, weights
+// dequantised straight into mma.sync B-fragment registers, M tiled in 64-row sub-problems that each
+// re-stream W). tcgen05 has no register operands, so the problem is TRANSPOSED and restructured:
+//
+//   D^T[128 out-channels, tokens<=256] += Wt[128 ch, 64 k] . A^T        one CTA per (128-channel tile,
+//                                                                        256-token block, k-split)
+//   * A (activations) : TMA tensor-map load (SWIZZLE_128B) of a [tokens x 64] bf16 box = the MMA "B"
+//                       operand (N = tokens, K-major). All tokens ride in ONE instruction (N <= 256), so W is
+//                       dequantised once per CTA, not once per 64 rows of M.
+//   * W (packed int4) : the Marlin tile rows of this channel tile are contiguous 1 KB runs -> cp.async.bulk
+//                       into an 8-deep ring; four dequant warps read one uint4 per lane (= a lane's four
+//                       mma.sync fragments in Marlin's layout), extract nibble PAIRS with lop3 in Marlin's
+//                       interleaved order, subtract the bias / zero point exactly, multiply by the group scale
+//                       (one rounding: bit-identical to the reference's w = T((q-8)*s)), and st.shared the
+//                       result into a SWIZZLE_128B K-major tile = the MMA "A" operand (M = 128 channels).
+//                       The lane->(row,k) mapping makes those stores bank-conflict free.
+//   * MMA             : one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=tokens, K=16) x4
+//                       per stage, accumulating in TMEM; tcgen05.commit releases the stage / publishes the tile.
+//   * epilogue        : the dequant warps tcgen05.ld their TMEM lane quadrant (lane = channel, column = token),
+//                       convert and store C (or red.add into the fp32 split-k buffer).
+#include "common.cuh"
+
+#include <cuda.h>
+
+#include <type_traits>
+
+namespace b200 {
+
+static constexpr int MG_NT = 128;        // output channels per CTA  (UMMA M)
+static constexpr int MG_KC = 64;         // k per stage (one 128-byte swizzle row of 16-bit elements)
+static constexpr int MG_TOK = 256;       // max tokens per CTA       (UMMA N)
+static constexpr int MG_STAGES = 3;      // (activation tile + dequantised weight tile) stages
+static constexpr int MG_PK_STAGES = 8;   // packed-weight ring
+static constexpr int MG_THREADS = 7 * 32;
+static constexpr int MG_ACT_BYTES = MG_TOK * 128;  // 32 KB
+static constexpr int MG_W_BYTES = MG_NT * 128;     // 16 KB
+static constexpr int MG_PK_BYTES = 4 * 256 * 4;    // 4 k-tiles x 256 words
+static constexpr int MG_SMEM = MG_STAGES * (MG_ACT_BYTES + MG_W_BYTES) + MG_PK_STAGES * MG_PK_BYTES +
+                               512 /*barriers*/ + 1024 /*alignment slack*/;
+
+struct MarlinParams {
+  const uint32_t* b_q;   // [K/16, N*2] int32, Marlin layout
+  const void* scales;    // [groups, N] T, Marlin-permuted
+  const uint32_t* zeros; // [groups, N/8] int32 (AWQ) or nullptr
+  void* c;               // [M, N] T
+  float* c_tmp;          // [M, N] fp32, zero-initialised (split-k only)
+  int M, N, K;
+  int group_size;        // -1 = channel-wise (single scale row)
+  int chunks_per_split;  // 64-wide k chunks handled by one CTA
+  int split_k;
+  int box_rows;          // rows of the activation TMA box (tokens rounded up to 16, <= 256)
+};
+
+// ---- PTX wrappers -------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar,
+                                            int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_plain(void* smem_dst, const void* gmem_src, uint32_t bytes,
+                                               uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+//   [0,14) start>>4, [16,30) LBO>>4 (unused for swizzled K-major: 1), [32,46) SBO>>4 (8 rows x 128 B = 1024),
+//   [46,48) version = 1 (Blackwell), [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+         (2ull << 61);
+}
+
+template <typename T> struct DQ;  // magic numbers of the int4 -> 16-bit float trick (exact integers)
+template <> struct DQ<__nv_bfloat16> {
+  static constexpr uint32_t MAGIC = 0x43004300u;          // 128.0 | 128.0 : 128 + q is exact (q < 128)
+  static __device__ __forceinline__ uint32_t offset(int q) {  // bf16x2 of (128 + q)
+    const uint32_t h = 0x4300u + (uint32_t)q;                 // 128+q: mantissa lsb = 1 in [128,256)
+    return h | (h << 16);
+  }
+  static __device__ __forceinline__ uint32_t sub_mul(uint32_t x, uint32_t off, uint32_t s2) {
+    __nv_bfloat162 v = __hsub2(*reinterpret_cast<__nv_bfloat162*>(&x), *reinterpret_cast<__nv_bfloat162*>(&off));
+    v = __hmul2(v, *reinterpret_cast<__nv_bfloat162*>(&s2));
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+};
+template <> struct DQ<__half> {
+  static constexpr uint32_t MAGIC = 0x64006400u;          // 1024.0 | 1024.0
+  static __device__ __forceinline__ uint32_t offset(int q) {
+    const uint32_t h = 0x6400u + (uint32_t)q;                 // 1024+q exact
+    return h | (h << 16);
+  }
+  static __device__ __forceinline__ uint32_t sub_mul(uint32_t x, uint32_t off, uint32_t s2) {
+    __half2 v = __hsub2(*reinterpret_cast<__half2*>(&x), *reinterpret_cast<__half2*>(&off));
+    v = __hmul2(v, *reinterpret_cast<__half2*>(&s2));
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+};
+
+__device__ __forceinline__ uint32_t lop3_and_or(uint32_t a, uint32_t b, uint32_t c) {  // (a & b) | c
+  uint32_t r;
+  asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
+}
+
+// position of output column n (0..N) inside a Marlin-permuted scale row
+// (aphrodite/quantization/utils/marlin_utils.py:172-196)
+__device__ __forceinline__ int scale_pos(int n, bool grouped) {
+  if (grouped) return (n & ~63) + 8 * (n & 7) + ((n & 63) >> 3);
+  return (n & ~31) + 8 * ((n & 7) >> 1) + 2 * ((n & 31) >> 3) + (n & 1);
+}
+
+template <typename T, bool HAS_ZP>
+__global__ void __launch_bounds__(MG_THREADS, 1)
+marlin_w4a16_tc5_kernel(const __grid_constant__ CUtensorMap tmap_a, const MarlinParams p) {
+  extern __shared__ uint8_t mg_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(mg_smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* act_s = smem;                                       // [STAGES][256 x 128 B]
+  uint8_t* w_s = act_s + MG_STAGES * MG_ACT_BYTES;             // [STAGES][128 x 128 B]
+  uint8_t* pk_s = w_s + MG_STAGES * MG_W_BYTES;                // [PK_STAGES][4 KB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(pk_s + MG_PK_STAGES * MG_PK_BYTES);
+  uint64_t* full_act = bars;                       // [STAGES]  TMA tx
+  uint64_t* full_w = full_act + MG_STAGES;         // [STAGES]  4 dequant warps
+  uint64_t* empty = full_w + MG_STAGES;            // [STAGES]  tcgen05.commit
+  uint64_t* pk_full = empty + MG_STAGES;           // [PK_STAGES]
+  uint64_t* pk_empty = pk_full + MG_PK_STAGES;     // [PK_STAGES] 4 dequant warps
+  uint64_t* accum_full = pk_empty + MG_PK_STAGES;  // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_base = blockIdx.x * MG_NT;
+  const int tok_base = blockIdx.y * MG_TOK;
+  const int toks = min(MG_TOK, p.M - tok_base);
+  const int n_mma = (toks + 15) & ~15;                       // UMMA N (multiple of 16, <= 256)
+  const int nblk = min(2, (p.N - n_base) / 64);              // 16x64 Marlin blocks in this channel tile
+  const int total_chunks = p.K / MG_KC;
+  const int chunk0 = blockIdx.z * p.chunks_per_split;
+  const int nchunks = min(p.chunks_per_split, total_chunks - chunk0);
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < n_mma) tmem_cols <<= 1;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < MG_STAGES; ++i) {
+      mbar_init(&full_act[i], 1);
+      mbar_init(&full_w[i], 4);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < MG_PK_STAGES; ++i) {
+      mbar_init(&pk_full[i], 1);
+      mbar_init(&pk_empty[i], 4);
+    }
+    mbar_init(accum_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot;
+
+  if (nchunks > 0) {
+    if (warp == 0) {
+      // ===================== activation TMA producer =====================
+      if (lane == 0) {
+        for (int c = 0; c < nchunks; ++c) {
+          const int s = c % MG_STAGES;
+          const uint32_t use = (uint32_t)(c / MG_STAGES);
+          mbar_wait(&empty[s], (use & 1u) ^ 1u);
+          mbar_arrive_expect_tx(&full_act[s], (uint32_t)p.box_rows * 128u);  // TMA always moves the full box
+          tma_load_2d(act_s + (size_t)s * MG_ACT_BYTES, &tmap_a, &full_act[s], (chunk0 + c) * MG_KC, tok_base);
+        }
+      }
+    } else if (warp == 1) {
+      // ===================== MMA issuer =====================
+      if (lane == 0) {
+        // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A/B = T, both K-major, N, M = 128
+        const uint32_t fmt = std::is_same<T, __nv_bfloat16>::value ? 1u : 0u;   // 0 = F16, 1 = BF16
+        const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n_mma >> 3) << 17) |
+                               ((uint32_t)(MG_NT >> 4) << 24);
+        for (int c = 0; c < nchunks; ++c) {
+          const int s = c % MG_STAGES;
+          const uint32_t par = (uint32_t)(c / MG_STAGES) & 1u;
+          mbar_wait(&full_act[s], par);
+          mbar_wait(&full_w[s], par);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(w_s + (size_t)s * MG_W_BYTES);
+          const uint32_t b_addr = smem_u32(act_s + (size_t)s * MG_ACT_BYTES);
+#pragma unroll
+          for (int ks = 0; ks < MG_KC / 16; ++ks) {
+            umma_f16(tmem_d, make_sw128_desc(a_addr + ks * 32), make_sw128_desc(b_addr + ks * 32), idesc,
+                     (c > 0 || ks > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty[s]);                  // frees act/w stage s when these MMAs retire
+        }
+        umma_commit(accum_full);                   // accumulator complete
+      }
+    } else if (warp == 2) {
+      // ===================== packed-weight producer =====================
+      if (lane == 0) {
+        const int row_words = p.N * 2;             // int32 per 16-row k-tile
+        const uint32_t bytes = (uint32_t)nblk * 512u;
+        for (int c = 0; c < nchunks; ++c) {
+          const int ps = c % MG_PK_STAGES;
+          const uint32_t use = (uint32_t)(c / MG_PK_STAGES);
+          mbar_wait(&pk_empty[ps], (use & 1u) ^ 1u);
+          mbar_arrive_expect_tx(&pk_full[ps], 4u * bytes);
+          const uint32_t* src = p.b_q + (size_t)((chunk0 + c) * 4) * row_words + (size_t)(n_base / 64) * 128;
+          uint8_t* dst = pk_s + (size_t)ps * MG_PK_BYTES;
+#pragma unroll
+          for (int kt = 0; kt < 4; ++kt)
+            bulk_g2s_plain(dst + kt * 1024, src + (size_t)kt * row_words, bytes, &pk_full[ps]);
+        }
+      }
+    } else {
+      // ===================== dequant warps (k-tile `dq` of every chunk) =====================
+      const int dq = warp - 3;
+      const int m = lane & 3, cq = lane >> 2;
+      const bool grouped = p.group_size > 0 && p.group_size < p.K;
+      const T* sc = reinterpret_cast<const T*>(p.scales);
+      uint32_t s2[2][8];    // per Marlin block: scale pairs {s,s} for column (j, b) at index 2j+b
+      uint32_t off2[2][8];  // per column: 16-bit pair of MAGIC + (8 | zero point)
+#pragma unroll
+      for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { s2[nb][e] = 0; off2[nb][e] = DQ<T>::offset(8); }
+      int cur_group = -2;
+      for (int c = 0; c < nchunks; ++c) {
+        const int ps = c % MG_PK_STAGES;
+        mbar_wait(&pk_full[ps], (uint32_t)(c / MG_PK_STAGES) & 1u);
+        const uint4* pk = reinterpret_cast<const uint4*>(pk_s + (size_t)ps * MG_PK_BYTES + dq * 1024);
+        uint4 q[2];
+        q[0] = pk[lane];
+        q[1] = (nblk > 1) ? pk[32 + lane] : make_uint4(0, 0, 0, 0);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&pk_empty[ps]);
+
+        // group parameters of this k-tile
+        const int kglob = (chunk0 + c) * MG_KC + dq * 16;
+        const int g = grouped ? kglob / p.group_size : 0;
+        if (g != cur_group) {
+          cur_group = g;
+          for (int nb = 0; nb < nblk; ++nb) {
+            const int col0 = n_base + nb * 64 + cq;
+            uint32_t zword = 0;
+            if (HAS_ZP) zword = p.zeros[(size_t)g * (p.N / 8) + (n_base + nb * 64) / 8 + cq];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {      // e = 2j + b  <->  column col0 + 16j + 8b
+              const int n = col0 + 16 * (e >> 1) + 8 * (e & 1);
+              const T sv = sc[(size_t)g * p.N + scale_pos(n, grouped)];
+              const uint32_t s16 = *reinterpret_cast<const uint16_t*>(&sv);
+              s2[nb][e] = s16 | (s16 << 16);
+              if (HAS_ZP) {
+                const int nib = ((e & 1) << 2) | (e >> 1);
+                off2[nb][e] = DQ<T>::offset((int)((zword >> (4 * nib)) & 0xFu));
+              }
+            }
+          }
+        }
+
+        const int s = c % MG_STAGES;
+        mbar_wait(&empty[s], ((uint32_t)(c / MG_STAGES) & 1u) ^ 1u);   // stage's previous MMAs retired
+        uint8_t* wt = w_s + (size_t)s * MG_W_BYTES;
+        const uint32_t a0 = (uint32_t)(((2 * dq) ^ cq) << 4) + 4u * m;       // k = 16dq + 2m (+1)
+        const uint32_t a1 = (uint32_t)(((2 * dq + 1) ^ cq) << 4) + 4u * m;   // k = 16dq + 8 + 2m (+1)
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb) {
+          if (nb < nblk) {
+            const uint32_t wq[4] = {q[nb].x, q[nb].y, q[nb].z, q[nb].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t w = wq[j];
+              const int row0 = nb * 64 + 16 * j + cq;
+              uint8_t* r0 = wt + row0 * 128;
+              uint8_t* r1 = r0 + 8 * 128;
+              const uint32_t x00 = lop3_and_or(w, 0x000f000fu, DQ<T>::MAGIC);
+              const uint32_t x01 = lop3_and_or(w >> 4, 0x000f000fu, DQ<T>::MAGIC);
+              const uint32_t x10 = lop3_and_or(w >> 8, 0x000f000fu, DQ<T>::MAGIC);
+              const uint32_t x11 = lop3_and_or(w >> 12, 0x000f000fu, DQ<T>::MAGIC);
+              *reinterpret_cast<uint32_t*>(r0 + a0) = DQ<T>::sub_mul(x00, off2[nb][2 * j], s2[nb][2 * j]);
+              *reinterpret_cast<uint32_t*>(r0 + a1) = DQ<T>::sub_mul(x01, off2[nb][2 * j], s2[nb][2 * j]);
+              *reinterpret_cast<uint32_t*>(r1 + a0) = DQ<T>::sub_mul(x10, off2[nb][2 * j + 1], s2[nb][2 * j + 1]);
+              *reinterpret_cast<uint32_t*>(r1 + a1) = DQ<T>::sub_mul(x11, off2[nb][2 * j + 1], s2[nb][2 * j + 1]);
+            }
+          }
+        }
+        fence_proxy_async();          // generic-proxy stores -> visible to the tensor core's async proxy
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_w[s]);
+      }
+
+      // ===================== epilogue: TMEM -> C =====================
+      mbar_wait(accum_full, 0);
+      tc_fence_after();
+      const int quad = warp & 3;                            // TMEM lanes 32*quad .. +31 belong to this warp
+      const int ch = n_base + quad * 32 + lane;
+      const bool ch_ok = ch < p.N;
+      T* cptr = reinterpret_cast<T*>(p.c);
+      for (int col0 = 0; col0 < n_mma; col0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)col0, v);
+        if (ch_ok) {
+#pragma unroll
+          for (int t = 0; t < 32; ++t) {
+            const int tok = tok_base + col0 + t;
+            if (col0 + t < toks) {
+              const float f = __uint_as_float(v[t]);
+              if (p.split_k > 1) atomicAdd(p.c_tmp + (size_t)tok * p.N + ch, f);
+              else cptr[(size_t)tok * p.N + ch] = from_f32<T>(f);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+    }
+  }
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_d, tmem_cols);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+splitk_convert_kernel(T* __restrict__ c, const float* __restrict__ c_tmp, int64_t numel) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += (int64_t)gridDim.x * blockDim.x)
+    c[i] = from_f32<T>(c_tmp[i]);
+}
+
+// ---- host -----------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+static int plan_split_k(int M, int N, int K, int group_size) {
+  const int tiles = ((N + MG_NT - 1) / MG_NT) * ((M + MG_TOK - 1) / MG_TOK);
+  const int chunks = K / MG_KC;
+  int split = 1;
+  const int sms = num_sms();
+  while (tiles * split * 2 <= sms && chunks / (split * 2) >= 8) split *= 2;
+  // keep every split on a group boundary
+  const int gchunks = group_size > MG_KC ? group_size / MG_KC : 1;
+  while (split > 1 && ((chunks + split - 1) / split) % gchunks != 0) split /= 2;
+  return split;
+}
+
+template <typename T, bool HAS_ZP>
+static int launch_marlin(const CUtensorMap& tmap, const MarlinParams& p, cudaStream_t st) {
+  auto kern = marlin_w4a16_tc5_kernel<T, HAS_ZP>;
+  static thread_local uint64_t attr_done = 0;
+  int dev = 0;
+  B200_CUDA_OK(cudaGetDevice(&dev));
+  if (!(attr_done >> (dev & 63) & 1)) {
+    B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_SMEM));
+    attr_done |= 1ull << (dev & 63);
+  }
+  dim3 grid((p.N + MG_NT - 1) / MG_NT, (p.M + MG_TOK - 1) / MG_TOK, p.split_k);
+  kern<<<grid, MG_THREADS, MG_SMEM, st>>>(tmap, p);
+  return check_launch("marlin_w4a16_tc5_kernel");
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_marlin_gemm_plan(int size_m, int size_n, int size_k, int num_groups) {
+  const int gs = num_groups > 1 ? size_k / num_groups : -1;
+  if (size_m <= 0 || size_n <= 0 || size_k < MG_KC) return 1;
+  return plan_split_k(size_m, size_n, size_k, gs);
+}
+
+extern "C" int b200_gptq_marlin_gemm(const void* a, const void* b_q_weight, const void* b_scales,
+                                     const void* b_zeros, void* c, float* c_tmp, int size_m, int size_n,
+                                     int size_k, int num_groups, int num_bits, int has_zp, int dtype,
+                                     int split_k, void* stream) {
+  B200_CHECK(dtype == B200_F16 || dtype == B200_BF16, "gpt_marlin_gemm only supports bfloat16 and float16");
+  B200_CHECK(num_bits == 4, "b200 marlin gemm: only 4-bit weights (uint4b8 / uint4) are implemented");
+  B200_CHECK(size_n % 64 == 0, "size_n = " + std::to_string(size_n) + ", is not divisible by min_thread_n = 64");
+  B200_CHECK(size_k % MG_KC == 0, "size_k = " + std::to_string(size_k) + " is not divisible by 64");
+  B200_CHECK(num_groups >= 1 && size_k % num_groups == 0, "size_k is not divisible by the number of scale groups");
+  const int gs = num_groups > 1 ? size_k / num_groups : -1;
+  B200_CHECK(gs == -1 || gs % 16 == 0, "unsupported group size " + std::to_string(gs));
+  B200_CHECK(!has_zp || b_zeros != nullptr, "has_zp requires b_zeros");
+  B200_CHECK((reinterpret_cast<uintptr_t>(a) & 15) == 0 && (reinterpret_cast<uintptr_t>(b_q_weight) & 15) == 0,
+             "a and b_q_weight must be 16-byte aligned");
+  if (size_m == 0) return 0;
+  if (split_k <= 0) split_k = plan_split_k(size_m, size_n, size_k, gs);
+  B200_CHECK(split_k == 1 || c_tmp != nullptr, "split-k needs the zero-initialised fp32 reduce buffer");
+  EncodeTiledFn enc = get_encode();
+  B200_CHECK(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+
+  const int toks = size_m < MG_TOK ? size_m : MG_TOK;
+  const int box_rows = (toks + 15) & ~15;
+  CUtensorMap tmap;
+  const cuuint64_t gdim[2] = {(cuuint64_t)size_k, (cuuint64_t)size_m};
+  const cuuint64_t gstride[1] = {(cuuint64_t)size_k * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)MG_KC, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(&tmap, dtype == B200_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+                         2, const_cast<void*>(a), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  B200_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed: " + std::to_string((int)r));
+
+  MarlinParams p{};
+  p.b_q = (const uint32_t*)b_q_weight; p.scales = b_scales; p.zeros = (const uint32_t*)b_zeros;
+  p.c = c; p.c_tmp = c_tmp; p.M = size_m; p.N = size_n; p.K = size_k; p.group_size = gs;
+  p.split_k = split_k;
+  p.box_rows = box_rows;
+  const int chunks = size_k / MG_KC;
+  p.chunks_per_split = (chunks + split_k - 1) / split_k;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  if (dtype == B200_BF16)
+    rc = has_zp ? launch_marlin<__nv_bfloat16, true>(tmap, p, st) : launch_marlin<__nv_bfloat16, false>(tmap, p, st);
+  else
+    rc = has_zp ? launch_marlin<__half, true>(tmap, p, st) : launch_marlin<__half, false>(tmap, p, st);
+  if (rc != 0) return rc;
+  if (split_k > 1) {
+    const int64_t numel = (int64_t)size_m * size_n;
+    int blocks = (int)((numel + 255) / 256 < (int64_t)num_sms() * 8 ? (numel + 255) / 256 : (int64_t)num_sms() * 8);
+    if (dtype == B200_BF16)
+      splitk_convert_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((__nv_bfloat16*)c, c_tmp, numel);
+    else
+      splitk_convert_kernel<__half><<<blocks, 256, 0, st>>>((__half*)c, c_tmp, numel);
+    return check_launch("splitk_convert_kernel");
+  }
+  return 0;
+}

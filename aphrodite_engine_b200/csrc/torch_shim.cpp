@@ -13,6 +13,8 @@
 #include <c10/cuda/CUDAGuard.h>
 #include <torch/all.h>
 #include <torch/library.h>
+#include <torch/custom_class.h>
+#include <ATen/core/stack.h>
 
 #include <string>
 #include <vector>
@@ -253,6 +255,167 @@ int64_t get_max_shared_memory_per_block_device_attribute(int64_t device_id) {
   return b200_get_max_shared_memory_per_block_device_attribute(device_id);
 }
 
+
+// ---- Marlin-format quantised GEMM ------------------------------------------------------------------
+// `b_q_type` is a `_core_C.ScalarType` custom-class object. It is read through the class's registered
+// property getters (size_bits, bias), NOT through a C++ type, so this op works with either this repo's
+// `_core_C` (csrc/core_scalar_type.cpp) or the reference's own `_core_C` extension.
+int64_t scalar_type_prop(const c10::IValue& st, const char* name) {
+  auto obj = st.toObject();
+  auto prop = obj->type()->getProperty(name);
+  TORCH_CHECK(prop.has_value(), "b_q_type has no property '", name, "'");
+  return (*prop->getter)({st}).toInt();
+}
+
+torch::Tensor gptq_marlin_gemm_impl(torch::Tensor& a, torch::Tensor& b_q_weight, torch::Tensor& b_scales,
+                                    torch::Tensor& b_zeros, torch::Tensor& g_idx, torch::Tensor& perm,
+                                    torch::Tensor& workspace, int64_t type_bits, int64_t type_bias,
+                                    const std::string& type_str, int64_t size_m, int64_t size_n,
+                                    int64_t size_k, bool is_k_full, bool has_zp, bool use_fp32_reduce,
+                                    bool is_zp_float) {
+  // argument contract of the reference entry point (gptq_marlin.cu:2255-2405), same messages
+  if (has_zp) {
+    TORCH_CHECK(type_bias == 0 && (type_bits == 4 || type_bits == 8),
+                "b_q_type must be u4 or u8 when has_zp = True. Got = ", type_str);
+  } else {
+    TORCH_CHECK((type_bits == 4 && type_bias == 8) || (type_bits == 8 && type_bias == 128),
+                "b_q_type must be uint4b8 or uint8b128 when has_zp = False. Got = ", type_str);
+  }
+  TORCH_CHECK(!(has_zp && is_zp_float), "float zero points (HQQ) are not implemented in the B200 marlin kernel");
+  const int64_t pack_factor = 32 / type_bits;
+  TORCH_CHECK(a.size(0) == size_m, "Shape mismatch: a.size(0) = ", a.size(0), ", size_m = ", size_m);
+  TORCH_CHECK(a.size(1) == size_k, "Shape mismatch: a.size(1) = ", a.size(1), ", size_k = ", size_k);
+  TORCH_CHECK(size_k % 16 == 0, "size_k = ", size_k, " is not divisible by tile_size = 16");
+  TORCH_CHECK((size_k / 16) == b_q_weight.size(0), "Shape mismatch: b_q_weight.size(0) = ",
+              b_q_weight.size(0), ", size_k = ", size_k, ", tile_size = 16");
+  TORCH_CHECK(b_q_weight.size(1) % 16 == 0, "b_q_weight.size(1) = ", b_q_weight.size(1),
+              " is not divisible by tile_size = 16");
+  const int64_t actual_size_n = (b_q_weight.size(1) / 16) * pack_factor;
+  TORCH_CHECK(size_n == actual_size_n, "size_n = ", size_n, ", actual_size_n = ", actual_size_n);
+  TORCH_CHECK(a.device().is_cuda(), "A is not on GPU");
+  TORCH_CHECK(a.is_contiguous(), "A is not contiguous");
+  TORCH_CHECK(b_q_weight.device().is_cuda() && b_q_weight.is_contiguous(), "b_q_weight must be a contiguous GPU tensor");
+  TORCH_CHECK(b_scales.device().is_cuda() && b_scales.is_contiguous(), "b_scales must be a contiguous GPU tensor");
+  TORCH_CHECK((g_idx.size(0) == 0 && perm.size(0) == 0) || (g_idx.size(0) == size_k && perm.size(0) == size_k),
+              "Unexpected g_idx.size(0) = ", g_idx.size(0), " and perm.size(0) = ", perm.size(0),
+              ", where size_k = ", size_k);
+  TORCH_CHECK(g_idx.size(0) == 0, "act_order (g_idx / perm) is not implemented in the B200 marlin kernel");
+  TORCH_CHECK(b_scales.dim() == 2, "b_scales rank = ", b_scales.dim(), " is not 2");
+  TORCH_CHECK(b_scales.size(1) == size_n, "b_scales dim 1 = ", b_scales.size(1), " is not size_n = ", size_n);
+  const int64_t num_groups = b_scales.size(0);
+  if (num_groups > 1)
+    TORCH_CHECK(size_k % num_groups == 0, "size_k = ", size_k, ", is not divisible by b_scales.size(0) = ", num_groups);
+  if (has_zp) {
+    TORCH_CHECK(b_zeros.dim() == 2, "b_zeros rank = ", b_zeros.dim(), " is not 2");
+    TORCH_CHECK(b_zeros.size(0) == num_groups, "b_zeros dim 0 = ", b_zeros.size(0), " is not num_groups = ", num_groups);
+    TORCH_CHECK(b_zeros.size(1) == size_n / pack_factor, "b_zeros dim 1 = ", b_zeros.size(1),
+                " is not size_n / pack_factor = ", size_n / pack_factor);
+  }
+  TORCH_CHECK(size_n % 64 == 0, "size_n = ", size_n, ", is not divisible by min_thread_n = 64");
+  const int64_t min_workspace_size = (size_n / 64) * 16;
+  TORCH_CHECK(workspace.numel() >= min_workspace_size, "workspace.numel = ", workspace.numel(),
+              " is below min_workspace_size = ", min_workspace_size);
+  TORCH_CHECK(a.scalar_type() == at::kHalf || a.scalar_type() == at::kBFloat16,
+              "gpt_marlin_gemm only supports bfloat16 and float16");
+  TORCH_CHECK(b_scales.scalar_type() == a.scalar_type(), "b_scales must have the dtype of a");
+
+  const at::cuda::OptionalCUDAGuard guard(device_of(a));
+  torch::Tensor c = torch::empty({size_m, size_n}, a.options());
+  if (size_m == 0) return c;
+  const int split = b200_marlin_gemm_plan((int)size_m, (int)size_n, (int)size_k, (int)num_groups);
+  torch::Tensor c_tmp;
+  float* c_tmp_ptr = nullptr;
+  if (split > 1) {  // the reference's fp32 global-reduce buffer (gptq_marlin.cu:2317-2327), zeroed here
+    c_tmp = torch::zeros({size_m, size_n}, a.options().dtype(at::kFloat));
+    c_tmp_ptr = c_tmp.data_ptr<float>();
+  }
+  (void)use_fp32_reduce; (void)is_k_full;
+  check(b200_gptq_marlin_gemm(a.data_ptr(), b_q_weight.data_ptr(), b_scales.data_ptr(),
+                              has_zp ? b_zeros.data_ptr() : nullptr, c.data_ptr(), c_tmp_ptr, (int)size_m,
+                              (int)size_n, (int)size_k, (int)num_groups, (int)type_bits, has_zp ? 1 : 0,
+                              dtype_code(a, "gptq_marlin_gemm"), split, cur_stream()));
+  return c;
+}
+
+void gptq_marlin_gemm_boxed(const c10::OperatorHandle&, torch::jit::Stack* stack) {
+  auto args = torch::jit::last(*stack, 15);
+  torch::Tensor a = args[0].toTensor(), bq = args[1].toTensor(), bs = args[2].toTensor(),
+                bz = args[3].toTensor(), gi = args[4].toTensor(), pm = args[5].toTensor(),
+                ws = args[6].toTensor();
+  const c10::IValue st = args[7];
+  const int64_t bits = scalar_type_prop(st, "size_bits"), bias = scalar_type_prop(st, "bias");
+  const std::string name = "ScalarType(size_bits=" + std::to_string(bits) + ", bias=" + std::to_string(bias) + ")";
+  torch::Tensor c = gptq_marlin_gemm_impl(a, bq, bs, bz, gi, pm, ws, bits, bias, name, args[8].toInt(),
+                                          args[9].toInt(), args[10].toInt(), args[11].toBool(),
+                                          args[12].toBool(), args[13].toBool(), args[14].toBool());
+  torch::jit::drop(*stack, 15);
+  torch::jit::push(*stack, std::move(c));
+}
+
+void moe_align_block_size(torch::Tensor topk_ids, int64_t num_experts, int64_t block_size,
+                          torch::Tensor sorted_token_ids, torch::Tensor experts_ids,
+                          torch::Tensor num_tokens_post_pad) {
+  const at::cuda::OptionalCUDAGuard guard(device_of(topk_ids));
+  TORCH_CHECK(topk_ids.scalar_type() == at::kInt || topk_ids.scalar_type() == at::kLong,
+              "moe_align_block_size: topk_ids must be int32 or int64");
+  TORCH_CHECK(topk_ids.is_contiguous(), "topk_ids must be contiguous");
+  check(b200_moe_align_block_size(topk_ids.data_ptr(), topk_ids.scalar_type() == at::kLong ? 1 : 0,
+                                  topk_ids.numel(), (int)num_experts, (int)block_size,
+                                  sorted_token_ids.data_ptr<int32_t>(), experts_ids.data_ptr<int32_t>(),
+                                  num_tokens_post_pad.data_ptr<int32_t>(), cur_stream()));
+}
+
+torch::Tensor gptq_marlin_repack(torch::Tensor& b_q_weight, torch::Tensor& perm, c10::SymInt size_k_s,
+                                 c10::SymInt size_n_s, int64_t num_bits) {
+  const int64_t size_k = size_k_s.expect_int(), size_n = size_n_s.expect_int();
+  TORCH_CHECK(num_bits == 4 || num_bits == 8, "num_bits must be 4 or 8. Got = ", num_bits);
+  const int64_t pf = 32 / num_bits;
+  TORCH_CHECK(size_k % 16 == 0, "size_k = ", size_k, " is not divisible by tile_k_size = 16");
+  TORCH_CHECK(size_n % 64 == 0, "size_n = ", size_n, " is not divisible by tile_n_size = 64");
+  TORCH_CHECK(b_q_weight.size(0) == size_k / pf, "Shape mismatch: b_q_weight.size(0) = ", b_q_weight.size(0),
+              ", size_k = ", size_k, ", pack_factor = ", pf);
+  TORCH_CHECK(b_q_weight.size(1) == size_n, "b_q_weight.size(1) = ", b_q_weight.size(1), " is not size_n = ", size_n);
+  TORCH_CHECK(b_q_weight.device().is_cuda() && b_q_weight.is_contiguous(), "b_q_weight must be a contiguous GPU tensor");
+  TORCH_CHECK(b_q_weight.dtype() == at::kInt, "b_q_weight type is not kInt");
+  TORCH_CHECK(perm.device().is_cuda() && perm.is_contiguous(), "perm must be a contiguous GPU tensor");
+  TORCH_CHECK(perm.dtype() == at::kInt, "perm type is not at::kInt");
+  TORCH_CHECK(perm.numel() == 0 || perm.numel() == size_k, "perm must be empty or have size_k entries");
+  const at::cuda::OptionalCUDAGuard guard(device_of(b_q_weight));
+  torch::Tensor out = torch::empty({size_k / 16, size_n * 16 / pf}, b_q_weight.options());
+  check(b200_gptq_marlin_repack(b_q_weight.data_ptr(), perm.numel() ? perm.data_ptr<int>() : nullptr,
+                                out.data_ptr(), (int)size_k, (int)size_n, (int)num_bits, cur_stream()));
+  return out;
+}
+torch::Tensor gptq_marlin_repack_meta(torch::Tensor& b_q_weight, torch::Tensor& perm, c10::SymInt size_k,
+                                      c10::SymInt size_n, int64_t num_bits) {
+  const int64_t pf = 32 / num_bits;
+  return torch::empty_symint({size_k / 16, size_n * 16 / pf}, b_q_weight.options());
+}
+
+torch::Tensor awq_marlin_repack(torch::Tensor& b_q_weight, c10::SymInt size_k_s, c10::SymInt size_n_s,
+                                int64_t num_bits) {
+  const int64_t size_k = size_k_s.expect_int(), size_n = size_n_s.expect_int();
+  TORCH_CHECK(num_bits == 4 || num_bits == 8, "num_bits must be 4 or 8. Got = ", num_bits);
+  const int64_t pf = 32 / num_bits;
+  TORCH_CHECK(size_k % 16 == 0, "size_k = ", size_k, " is not divisible by tile_k_size = 16");
+  TORCH_CHECK(size_n % 64 == 0, "size_n = ", size_n, " is not divisible by tile_n_size = 64");
+  TORCH_CHECK(b_q_weight.size(0) == size_k, "b_q_weight.size(0) = ", b_q_weight.size(0), " is not size_k = ", size_k);
+  TORCH_CHECK(b_q_weight.size(1) == size_n / pf, "Shape mismatch: b_q_weight.size(1) = ", b_q_weight.size(1),
+              ", size_n = ", size_n, ", pack_factor = ", pf);
+  TORCH_CHECK(b_q_weight.device().is_cuda() && b_q_weight.is_contiguous(), "b_q_weight must be a contiguous GPU tensor");
+  TORCH_CHECK(b_q_weight.dtype() == at::kInt, "b_q_weight type is not kInt");
+  const at::cuda::OptionalCUDAGuard guard(device_of(b_q_weight));
+  torch::Tensor out = torch::empty({size_k / 16, size_n * 16 / pf}, b_q_weight.options());
+  check(b200_awq_marlin_repack(b_q_weight.data_ptr(), out.data_ptr(), (int)size_k, (int)size_n, (int)num_bits,
+                               cur_stream()));
+  return out;
+}
+torch::Tensor awq_marlin_repack_meta(torch::Tensor& b_q_weight, c10::SymInt size_k, c10::SymInt size_n,
+                                     int64_t num_bits) {
+  const int64_t pf = 32 / num_bits;
+  return torch::empty_symint({size_k / 16, size_n * 16 / pf}, b_q_weight.options());
+}
+
 }  // namespace
 
 TORCH_LIBRARY(_C, ops) {
@@ -312,6 +475,34 @@ TORCH_LIBRARY(_C, ops) {
       "                         int rot_dim,"
       "                         Tensor cos_sin_cache_offsets) -> ()");
   ops.impl("batched_rotary_embedding", torch::kCUDA, &batched_rotary_embedding);
+
+  // Aligning the number of tokens to be processed by each expert (kernels/torch_bindings.cpp:394-399)
+  ops.def(
+      "moe_align_block_size(Tensor topk_ids, int num_experts,"
+      "                     int block_size, Tensor! sorted_token_ids,"
+      "                     Tensor! experts_ids,"
+      "                     Tensor! num_tokens_post_pad) -> ()");
+  ops.impl("moe_align_block_size", torch::kCUDA, &moe_align_block_size);
+
+  // Marlin-format weight-only quantised GEMM + repack (kernels/torch_bindings.cpp:195-215)
+  ops.def(
+      "gptq_marlin_gemm(Tensor a, Tensor b_q_weight, Tensor b_scales, "
+      "Tensor b_zeros, Tensor g_idx, Tensor perm, Tensor workspace, "
+      "__torch__.torch.classes._core_C.ScalarType b_q_type, "
+      "int size_m, int size_n, int size_k, bool is_k_full, "
+      "bool has_zp, bool use_fp32_reduce, bool is_zp_float) -> Tensor");
+  ops.impl("gptq_marlin_gemm", torch::dispatch(c10::DispatchKey::CUDA,
+           torch::CppFunction::makeFromBoxedFunction<&gptq_marlin_gemm_boxed>()));
+  ops.def(
+      "gptq_marlin_repack(Tensor b_q_weight, Tensor perm, "
+      "SymInt size_k, SymInt size_n, int num_bits) -> Tensor");
+  ops.impl("gptq_marlin_repack", torch::kCUDA, &gptq_marlin_repack);
+  ops.impl("gptq_marlin_repack", torch::kMeta, &gptq_marlin_repack_meta);
+  ops.def(
+      "awq_marlin_repack(Tensor b_q_weight, SymInt size_k, "
+      "SymInt size_n, int num_bits) -> Tensor");
+  ops.impl("awq_marlin_repack", torch::kCUDA, &awq_marlin_repack);
+  ops.impl("awq_marlin_repack", torch::kMeta, &awq_marlin_repack_meta);
 }
 
 TORCH_LIBRARY(_C_cache_ops, cache_ops) {

@@ -77,7 +77,7 @@ class ClockSampler:
         try:
             self.f = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=self.f,
+                                          "-i", str(self.index), "-lms", "50"], stdout=self.f,
                                          stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -377,7 +377,7 @@ def run_b200(args):
         "eager_step_ms": eager_step_ms,
     }
     traffic_file = os.path.join(ROOT, "profiles", "attention_traffic.json")
-    if os.path.exists(traffic_file):
+    if os.path.exists(traffic_file) and world == 1 and (args.batch, args.ctx, args.block_size, args.kv_cache_dtype) == (256, 4096, 16, "auto"):
         try:
             roofline["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")
         except Exception:
@@ -406,10 +406,15 @@ def run_b200(args):
         except Exception as e:  # never lose the GPU numbers to a host-side problem
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "error": repr(e)}
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
+        # Tear-down: NCCL communicators captured in a live CUDA graph can block destroy_process_group();
+        # everything has been measured and printed, so synchronise and leave without running destructors.
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

@@ -148,6 +148,42 @@ int b200_act_and_mul(void* out, const void* input, int num_tokens, int d, int ac
 int b200_activation(void* out, const void* input, int num_tokens, int d, int act,
                     int dtype, void* stream);
 
+/* ---- Marlin-format weight-only quantised GEMM -------------------------------------------------
+ * replaces gptq_marlin_gemm   kernels/quantization/gptq_marlin/gptq_marlin.cu:2247-2430
+ *                             (schema kernels/torch_bindings.cpp:195-201, prototype quant_ops.h:74-94)
+ *          gptq_marlin_repack kernels/quantization/gptq_marlin/gptq_marlin_repack.cu:271-343 (schema :204-208)
+ *          awq_marlin_repack  kernels/quantization/gptq_marlin/awq_marlin_repack.cu:208-268  (schema :211-215)
+ * a [size_m, size_k] f16/bf16 contiguous; b_q_weight int32 [size_k/16, size_n*16/pack] (Marlin tiles);
+ * b_scales [num_groups, size_n] (Marlin-permuted, num_groups == 1: channel-wise); b_zeros int32
+ * [num_groups, size_n/8] (AWQ integer zero points, Marlin layout) or NULL; c [size_m, size_n].
+ * c_tmp: fp32 [size_m, size_n], ZERO-INITIALISED, needed only when the plan splits k
+ * (b200_marlin_gemm_plan(...) > 1; the reference's use_fp32_reduce buffer, gptq_marlin.cu:2313-2327).
+ * split_k <= 0 = use the plan. 4-bit only (uint4b8, uint4+zp); act-order (g_idx/perm) is not supported. */
+int b200_marlin_gemm_plan(int size_m, int size_n, int size_k, int num_groups);
+int b200_gptq_marlin_gemm(const void* a, const void* b_q_weight, const void* b_scales,
+                          const void* b_zeros, void* c, float* c_tmp, int size_m, int size_n,
+                          int size_k, int num_groups, int num_bits, int has_zp, int dtype,
+                          int split_k, void* stream);
+/* b_q_weight: GPTQ int32 [size_k/pack, size_n]; perm: int32 [size_k] act-order sort indices or NULL;
+ * out: int32 [size_k/16, size_n*16/pack]. Bit-exact integer re-tiling. num_bits 4 or 8. */
+int b200_gptq_marlin_repack(const void* b_q_weight, const int32_t* perm, void* out, int size_k,
+                            int size_n, int num_bits, void* stream);
+/* b_q_weight: AWQ int32 [size_k, size_n/pack] (column-interleaved) */
+int b200_awq_marlin_repack(const void* b_q_weight, void* out, int size_k, int size_n, int num_bits,
+                           void* stream);
+
+/* ---- MoE routing --------------------------------------------------------------------------------
+ * replaces moe_align_block_size  kernels/moe/align_block_size_kernel.cu:111-133 (schema torch_bindings.cpp:394-399)
+ *          topk_softmax          kernels/moe/softmax.cu:496-518 (schema kernels/moe/torch_bindings.cpp:11-14)
+ * topk_ids: int32 or int64 [numel] expert id per (token, k) slot; sorted_token_ids int32 (pre-filled with
+ * numel by the caller, fused_moe.py:214-228), expert_ids int32 [max_blocks], num_tokens_post_pad int32 [1]. */
+int b200_moe_align_block_size(const void* topk_ids, int ids_are_int64, int64_t numel, int num_experts,
+                              int block_size, int32_t* sorted_token_ids, int32_t* expert_ids,
+                              int32_t* num_tokens_post_pad, void* stream);
+/* gating_output fp32 [num_tokens, num_experts]; outputs [num_tokens, topk] */
+int b200_topk_softmax(float* topk_weights, int32_t* topk_indices, int32_t* token_expert_indices,
+                      const float* gating_output, int num_tokens, int num_experts, int topk, void* stream);
+
 /* ---- device queries -----------------------------------------------------------------------------
  * replaces get_device_attribute / get_max_shared_memory_per_block_device_attribute
  *          kernels/cuda_utils_kernels.cu (schema torch_bindings.cpp:497-504) */

@@ -85,6 +85,30 @@ def build(force: bool = False) -> bool:
     return True
 
 
+def build_core_ext(force: bool = False):
+    """The reference's `_core_C` (ScalarType custom class, kernels/core/torch_bindings.cpp, plain g++)
+    into oracle/_ref/aphrodite_ext/_core_C.abi3.so — only needed to IMPORT the reference's Python
+    quantisation utilities when generating golden vectors (tests/golden/make_golden_marlin.py)."""
+    tgt = os.path.join(OUT, "aphrodite_ext", "_core_C.abi3.so")
+    if os.path.exists(tgt) and not force:
+        return tgt
+    src = os.path.join(REF, "kernels", "core", "torch_bindings.cpp")
+    if not os.path.exists(src):
+        return tgt if os.path.exists(tgt) else None
+    import torch
+
+    tdir = os.path.dirname(torch.__file__)
+    abi = int(torch._C._GLIBCXX_USE_CXX11_ABI)
+    os.makedirs(os.path.dirname(tgt), exist_ok=True)
+    _run(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-w", "-DTORCH_EXTENSION_NAME=_core_C",
+          f"-D_GLIBCXX_USE_CXX11_ABI={abi}", f"-I{REF}/kernels/core", f"-I{tdir}/include",
+          f"-I{tdir}/include/torch/csrc/api/include", f"-I{sysconfig.get_paths()['include']}", src,
+          f"-L{tdir}/lib", "-ltorch", "-ltorch_cpu", "-lc10", "-ltorch_python",
+          f"-Wl,-rpath,{tdir}/lib", "-o", tgt])
+    return tgt
+
+
 if __name__ == "__main__":
     ok = build(force="--force" in sys.argv)
+    print("reference _core_C:", build_core_ext(force="--force" in sys.argv))
     print("oracle/_ref:", "ready" if ok else "unavailable (no /root/reference and no prebuilt .so)")

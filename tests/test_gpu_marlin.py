@@ -1,0 +1,126 @@
+"""GPU parity: Marlin repack kernels (bit-exact) and the tcgen05 W4A16 GEMM vs the CPU oracle
+(oracle/marlin.py, pinned against the reference's Python by tests/test_oracle_marlin_cpu.py).
+Mirrors tests/kernels/test_marlin_gemm.py of the reference: repack equality (:127, :178) and
+GEMM error vs `a @ w_ref` (:236-254, mean relative error < 0.04 there; far tighter here because the
+dequantised weights are bit-identical to w_ref and only the fp32 accumulation order differs)."""
+import pytest
+import torch
+
+from oracle import marlin as om
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _types():
+    from aphrodite_engine_b200.scalar_type import scalar_types
+    return scalar_types
+
+
+@pytest.mark.parametrize("bits", [4, 8])
+@pytest.mark.parametrize("shape", [(128, 64), (256, 128), (1024, 448), (4096, 1024)])
+@pytest.mark.parametrize("act_order", [False, True])
+def test_gptq_marlin_repack_bit_exact(ops, bits, shape, act_order):
+    K, N = shape
+    g = torch.Generator().manual_seed(K + N + bits)
+    q_w = torch.randint(0, 1 << bits, (K, N), generator=g, dtype=torch.int32)
+    packed = om.pack_rows(q_w, bits)
+    perm = torch.randperm(K, generator=g).int() if act_order else torch.empty(0, dtype=torch.int32)
+    out = ops.gptq_marlin_repack(packed.to(DEV), perm.to(DEV), K, N, bits)
+    ref = om.gptq_marlin_repack(packed, perm if act_order else None, K, N, bits)
+    assert out.dtype == torch.int32 and tuple(out.shape) == (K // 16, N * 16 // (32 // bits))
+    assert torch.equal(out.cpu(), ref)
+
+
+@pytest.mark.parametrize("bits", [4, 8])
+@pytest.mark.parametrize("shape", [(128, 64), (512, 320), (4096, 1024)])
+def test_awq_marlin_repack_bit_exact(ops, bits, shape):
+    K, N = shape
+    g = torch.Generator().manual_seed(K * 3 + N + bits)
+    q_w = torch.randint(0, 1 << bits, (K, N), generator=g, dtype=torch.int32)
+    packed = om.awq_pack(q_w, bits)
+    out = ops.awq_marlin_repack(packed.to(DEV), K, N, bits)
+    assert torch.equal(out.cpu(), om.awq_marlin_repack(packed, K, N, bits))
+    assert torch.equal(out.cpu(), om.marlin_weights(q_w, bits))
+
+
+def _check_gemm(out, ref):
+    out, ref = out.float().cpu(), ref.float()
+    assert torch.isfinite(out).all()
+    scale = ref.abs().max().clamp(min=1e-6)
+    assert ((out - ref).abs().max() / scale) < 1e-2, float((out - ref).abs().max() / scale)
+    assert ((out - ref).abs().mean() / ref.abs().mean().clamp(min=1e-6)) < 2e-3
+
+
+def _workspace(N):
+    return torch.zeros((N // 64) * 16, dtype=torch.int32, device=DEV)
+
+
+GEMM_SHAPES = [  # (M, K, N)
+    (1, 128, 64), (7, 256, 128), (16, 512, 192), (33, 1024, 256), (100, 256, 448), (128, 2048, 512),
+    (256, 4096, 1024), (257, 512, 128), (300, 1024, 256), (513, 256, 64),
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("group_size", [-1, 32, 64, 128])
+@pytest.mark.parametrize("mkn", GEMM_SHAPES)
+def test_gptq_marlin_gemm_uint4b8(ops, dtype, group_size, mkn):
+    M, K, N = mkn
+    torch.manual_seed(M * 7 + K + N)
+    a = torch.randn(M, K).to(dtype)
+    w = torch.randn(K, N).to(dtype)
+    w_ref, mq, ms = om.marlin_quantize(w, 4, group_size)
+    empty = torch.empty(0, dtype=torch.int32, device=DEV)
+    out = ops.gptq_marlin_gemm(a.to(DEV), mq.to(DEV), ms.to(DEV), empty, empty, empty, _workspace(N),
+                               _types().uint4b8, M, N, K, True, False, True, False)
+    torch.cuda.synchronize()
+    assert out.shape == (M, N) and out.dtype == dtype
+    _check_gemm(out, om.marlin_gemm(a, w_ref))
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("group_size", [32, 128])
+@pytest.mark.parametrize("mkn", [(1, 128, 64), (48, 512, 256), (256, 1024, 512), (260, 256, 192)])
+def test_awq_marlin_gemm_uint4_zp(ops, dtype, group_size, mkn):
+    M, K, N = mkn
+    torch.manual_seed(M + K + N)
+    a = torch.randn(M, K).to(dtype)
+    w = torch.randn(K, N).to(dtype)
+    w_ref, mq, ms, mzp = om.awq_marlin_quantize(w, 4, group_size)
+    empty = torch.empty(0, dtype=torch.int32, device=DEV)
+    out = ops.gptq_marlin_gemm(a.to(DEV), mq.to(DEV), ms.to(DEV), mzp.to(DEV), empty, empty, _workspace(N),
+                               _types().uint4, M, N, K, True, True, True, False)
+    torch.cuda.synchronize()
+    _check_gemm(out, om.marlin_gemm(a, w_ref))
+
+
+def test_gemm_llama_shapes_split_k(ops, cabi):
+    """The four Llama-3-8B projections at M = 256 (BASELINE configs[2]); exercises the split-k plan."""
+    torch.manual_seed(0)
+    M = 256
+    for K, N in ((4096, 6144), (4096, 4096), (14336, 4096)):
+        a = (torch.randn(M, K) * 0.5).to(torch.bfloat16)
+        w = torch.randn(K, N).to(torch.bfloat16)
+        w_ref, mq, ms = om.marlin_quantize(w, 4, 128)
+        empty = torch.empty(0, dtype=torch.int32, device=DEV)
+        out = ops.gptq_marlin_gemm(a.to(DEV), mq.to(DEV), ms.to(DEV), empty, empty, empty, _workspace(N),
+                                   _types().uint4b8, M, N, K, True, False, True, False)
+        torch.cuda.synchronize()
+        _check_gemm(out, om.marlin_gemm(a, w_ref))
+
+
+def test_marlin_argument_errors(ops):
+    empty = torch.empty(0, dtype=torch.int32, device=DEV)
+    a = torch.zeros(4, 128, dtype=torch.bfloat16, device=DEV)
+    mq = torch.zeros(8, 128, dtype=torch.int32, device=DEV)
+    ms = torch.ones(1, 64, dtype=torch.bfloat16, device=DEV)
+    with pytest.raises(RuntimeError, match="b_q_type must be uint4b8 or uint8b128"):
+        ops.gptq_marlin_gemm(a, mq, ms, empty, empty, empty, _workspace(64), _types().uint4, 4, 64, 128,
+                             True, False, True, False)
+    with pytest.raises(RuntimeError, match="Shape mismatch: a.size\\(1\\)"):
+        ops.gptq_marlin_gemm(a, mq, ms, empty, empty, empty, _workspace(64), _types().uint4b8, 4, 64, 256,
+                             True, False, True, False)
+    with pytest.raises(RuntimeError, match="workspace.numel"):
+        ops.gptq_marlin_gemm(a, mq, ms, empty, empty, empty, torch.zeros(1, dtype=torch.int32, device=DEV),
+                             _types().uint4b8, 4, 64, 128, True, False, True, False)
