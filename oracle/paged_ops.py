@@ -344,3 +344,47 @@ def make_kv_cache(num_blocks: int, block_size: int, num_kv_heads: int, head_size
         k = fp8_quant(k.to(torch.float16), 1.0, kv_cache_dtype)
         v = fp8_quant(v.to(torch.float16), 1.0, kv_cache_dtype)
     return k.to(device), v.to(device)
+
+
+# ------------------------------------------------------------------------------------------------
+# MoE routing (kernels/moe/align_block_size_kernel.cu:22-110, kernels/moe/softmax.cu:107-161)
+# ------------------------------------------------------------------------------------------------
+def moe_align_block_size(topk_ids: torch.Tensor, num_experts: int, block_size: int,
+                         max_num_tokens_padded: Optional[int] = None):
+    """Stable counting sort of the flat (token, k) slots by expert, every expert segment padded to a
+    multiple of block_size. Returns (sorted_token_ids, expert_ids, num_tokens_post_pad) with untouched
+    entries equal to the caller-side presets (numel / -1), as fused_moe.py:214-228 allocates them."""
+    flat = topk_ids.flatten().tolist()
+    numel = len(flat)
+    if max_num_tokens_padded is None:
+        max_num_tokens_padded = numel + num_experts * (block_size - 1)
+    sorted_ids = torch.full((max_num_tokens_padded,), numel, dtype=torch.int32)
+    max_blocks = (max_num_tokens_padded + block_size - 1) // block_size
+    expert_ids = torch.full((max_blocks,), -1, dtype=torch.int32)
+    off = 0
+    for e in range(num_experts):
+        idx = [i for i, v in enumerate(flat) if v == e]       # increasing order == stable
+        sorted_ids[off:off + len(idx)] = torch.tensor(idx, dtype=torch.int32)
+        padded = (len(idx) + block_size - 1) // block_size * block_size
+        expert_ids[off // block_size:(off + padded) // block_size] = e
+        off += padded
+    return sorted_ids, expert_ids, torch.tensor([off], dtype=torch.int32)
+
+
+def topk_softmax(gating_output: torch.Tensor, topk: int):
+    """softmax over experts in fp32, then k rounds of arg-max (ties -> lowest expert id);
+    weights are the un-renormalised probabilities; token_expert_indices[t, k] = k * T + t."""
+    T, E = gating_output.shape
+    p = torch.softmax(gating_output.float(), dim=-1)
+    w = torch.empty(T, topk, dtype=torch.float32)
+    ids = torch.empty(T, topk, dtype=torch.int32)
+    src = torch.empty(T, topk, dtype=torch.int32)
+    work = p.clone()
+    for k in range(topk):
+        best = work.max(dim=-1).values
+        first = (work == best.unsqueeze(-1)).float().argmax(dim=-1)   # lowest index among ties
+        w[:, k] = best
+        ids[:, k] = first.int()
+        src[:, k] = k * T + torch.arange(T, dtype=torch.int32)
+        work[torch.arange(T), first] = -1.0
+    return w, ids, src
