@@ -36,10 +36,18 @@ static constexpr int MG_KC = 64;         // k per stage (one 128-byte swizzle ro
 static constexpr int MG_TOK = 256;       // max tokens per CTA       (UMMA N)
 static constexpr int MG_STAGES = 3;      // (activation tile + dequantised weight tile) stages
 static constexpr int MG_PK_STAGES = 8;   // packed-weight ring
-static constexpr int MG_THREADS = 7 * 32;
+static constexpr int MG_TEAMS = 2;        // dequant teams (4 warps each) working on alternate chunks
+static constexpr int MG_THREADS = (3 + 4 * MG_TEAMS) * 32;
 static constexpr int MG_ACT_BYTES = MG_TOK * 128;  // 32 KB
 static constexpr int MG_W_BYTES = MG_NT * 128;     // 16 KB
-static constexpr int MG_PK_BYTES = 4 * 256 * 4;    // 4 k-tiles x 256 words
+static constexpr int MG_PK_W_BYTES = 4 * 256 * 4;  // 4 k-tiles x 256 words of packed weights
+// every packed stage also carries the chunk's scale rows (<= 2 groups x 128 channels x 2 B) and zero-point
+// rows (<= 2 x 16 words), copied by the same producer on the same mbarrier: no global-load latency in the
+// dequant loop
+static constexpr int MG_PK_SC_OFF = MG_PK_W_BYTES;         // 2 x 256 B
+static constexpr int MG_PK_ZP_OFF = MG_PK_SC_OFF + 512;    // 2 x 64 B
+static constexpr int MG_PK_BYTES = MG_PK_ZP_OFF + 128;     // 4736 B (multiple of 64)
+static_assert(MG_PK_STAGES % MG_TEAMS == 0, "a packed stage must always be consumed by the same team");
 static constexpr int MG_SMEM = MG_STAGES * (MG_ACT_BYTES + MG_W_BYTES) + MG_PK_STAGES * MG_PK_BYTES +
                                512 /*barriers*/ + 1024 /*alignment slack*/;
 
@@ -48,12 +56,16 @@ struct MarlinParams {
   const void* scales;    // [groups, N] T, Marlin-permuted
   const uint32_t* zeros; // [groups, N/8] int32 (AWQ) or nullptr
   void* c;               // [M, N] T
-  float* c_tmp;          // [M, N] fp32, zero-initialised (split-k only)
+  float* c_tmp;          // [split_k, M, N] fp32 partial slabs (split-k only; no initialisation needed)
+  int* locks;            // >= tiles ints, zero on entry, returned to zero (the reference's `workspace`)
   int M, N, K;
   int group_size;        // -1 = channel-wise (single scale row)
   int chunks_per_split;  // 64-wide k chunks handled by one CTA
   int split_k;
   int box_rows;          // rows of the activation TMA box (tokens rounded up to 16, <= 256)
+  int grouped;           // 1: b_scales has one row per k-group (Marlin "grouped" permutation), 0: single row
+  int rows_per_chunk;    // scale rows a 64-wide chunk spans (1, or 2 when group_size == 32)
+  int chunks_per_group;  // 64-wide chunks per scale group (>= 1)
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
@@ -103,6 +115,22 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr)
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// explicit shared-state-space accesses: the 1024-B re-aligned dynamic smem pointer is a GENERIC pointer to
+// the compiler (it would emit LD.E/ST.E through the generic path, which showed up as long-scoreboard stalls)
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
 }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
@@ -245,17 +273,33 @@ marlin_w4a16_tc5_kernel(const __grid_constant__ CUtensorMap tmap_a, const Marlin
           const int ps = c % MG_PK_STAGES;
           const uint32_t use = (uint32_t)(c / MG_PK_STAGES);
           mbar_wait(&pk_empty[ps], (use & 1u) ^ 1u);
-          mbar_arrive_expect_tx(&pk_full[ps], 4u * bytes);
+          const uint32_t sc_bytes = (uint32_t)nblk * 128u;          // 64 channels x 2 B per Marlin block
+          const uint32_t zp_bytes = (uint32_t)nblk * 32u;           // 8 int32 per Marlin block
+          const int srows = p.grouped ? p.rows_per_chunk : 0;       // channel-wise scales are read once
+          mbar_arrive_expect_tx(&pk_full[ps], 4u * bytes + (uint32_t)srows * (sc_bytes + (HAS_ZP ? zp_bytes : 0u)));
           const uint32_t* src = p.b_q + (size_t)((chunk0 + c) * 4) * row_words + (size_t)(n_base / 64) * 128;
           uint8_t* dst = pk_s + (size_t)ps * MG_PK_BYTES;
 #pragma unroll
           for (int kt = 0; kt < 4; ++kt)
             bulk_g2s_plain(dst + kt * 1024, src + (size_t)kt * row_words, bytes, &pk_full[ps]);
+          const int g0 = p.rows_per_chunk == 2 ? (chunk0 + c) * 2 : (chunk0 + c) / p.chunks_per_group;
+          for (int r = 0; r < srows; ++r) {
+            bulk_g2s_plain(dst + MG_PK_SC_OFF + r * 256,
+                           reinterpret_cast<const uint8_t*>(p.scales) + ((size_t)(g0 + r) * p.N + n_base) * 2,
+                           sc_bytes, &pk_full[ps]);
+            if (HAS_ZP)
+              bulk_g2s_plain(dst + MG_PK_ZP_OFF + r * 64, p.zeros + (size_t)(g0 + r) * (p.N / 8) + n_base / 8,
+                             zp_bytes, &pk_full[ps]);
+          }
         }
       }
     } else {
-      // ===================== dequant warps (k-tile `dq` of every chunk) =====================
-      const int dq = warp - 3;
+      // ===================== dequant warps: team `team` takes chunks team, team+TEAMS, ...; inside a
+      // team warp `dq` owns k-tile dq of the chunk. Two teams overlap one chunk's barrier / fence latency
+      // with the other's ALU work. (Each team's waits on a stage are chained through its own previous
+      // chunks, so no parity test can pass vacuously — see the attention kernel's ring invariant.)
+      const int team = (warp - 3) >> 2;
+      const int dq = (warp - 3) & 3;
       const int m = lane & 3, cq = lane >> 2;
       const bool grouped = p.group_size > 0 && p.group_size < p.K;
       const T* sc = reinterpret_cast<const T*>(p.scales);
@@ -265,43 +309,53 @@ marlin_w4a16_tc5_kernel(const __grid_constant__ CUtensorMap tmap_a, const Marlin
       for (int nb = 0; nb < 2; ++nb)
 #pragma unroll
         for (int e = 0; e < 8; ++e) { s2[nb][e] = 0; off2[nb][e] = DQ<T>::offset(8); }
-      int cur_group = -2;
-      for (int c = 0; c < nchunks; ++c) {
+      if (!grouped) {
+        // channel-wise: one scale row (and zero-point row) for the whole k range, read once
+        for (int nb = 0; nb < nblk; ++nb) {
+          const int col0 = n_base + nb * 64 + cq;
+          uint32_t zword = 0;
+          if (HAS_ZP) zword = p.zeros[(n_base + nb * 64) / 8 + cq];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {      // e = 2j + b  <->  column col0 + 16j + 8b
+            const int n = col0 + 16 * (e >> 1) + 8 * (e & 1);
+            const T sv = sc[scale_pos(n, false)];
+            const uint32_t s16 = *reinterpret_cast<const uint16_t*>(&sv);
+            s2[nb][e] = s16 | (s16 << 16);
+            if (HAS_ZP) off2[nb][e] = DQ<T>::offset((int)((zword >> (4 * (((e & 1) << 2) | (e >> 1)))) & 0xFu));
+          }
+        }
+      }
+      const int my_row = p.rows_per_chunk == 2 ? (dq >> 1) : 0;   // group_size 32: k-tiles 0,1 | 2,3
+      const uint32_t pk_addr = smem_u32(pk_s), w_addr = smem_u32(w_s);
+      for (int c = team; c < nchunks; c += MG_TEAMS) {
         const int ps = c % MG_PK_STAGES;
         mbar_wait(&pk_full[ps], (uint32_t)(c / MG_PK_STAGES) & 1u);
-        const uint4* pk = reinterpret_cast<const uint4*>(pk_s + (size_t)ps * MG_PK_BYTES + dq * 1024);
+        const uint32_t stage = pk_addr + (uint32_t)ps * MG_PK_BYTES;
         uint4 q[2];
-        q[0] = pk[lane];
-        q[1] = (nblk > 1) ? pk[32 + lane] : make_uint4(0, 0, 0, 0);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&pk_empty[ps]);
-
-        // group parameters of this k-tile
-        const int kglob = (chunk0 + c) * MG_KC + dq * 16;
-        const int g = grouped ? kglob / p.group_size : 0;
-        if (g != cur_group) {
-          cur_group = g;
+        q[0] = lds128(stage + dq * 1024 + lane * 16);
+        q[1] = (nblk > 1) ? lds128(stage + dq * 1024 + 512 + lane * 16) : make_uint4(0, 0, 0, 0);
+        if (grouped) {
+          // Marlin's grouped scale permutation puts this lane's 8 scales (columns 16j + 8b + cq of a block)
+          // in 16 contiguous bytes at position 8*cq of the block's 64-entry row; zero points: one int32
           for (int nb = 0; nb < nblk; ++nb) {
-            const int col0 = n_base + nb * 64 + cq;
+            const uint4 sv = lds128(stage + MG_PK_SC_OFF + my_row * 256 + nb * 128 + cq * 16);
+            const uint32_t sw[4] = {sv.x, sv.y, sv.z, sv.w};
             uint32_t zword = 0;
-            if (HAS_ZP) zword = p.zeros[(size_t)g * (p.N / 8) + (n_base + nb * 64) / 8 + cq];
+            if (HAS_ZP) zword = lds32(stage + MG_PK_ZP_OFF + my_row * 64 + nb * 32 + cq * 4);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {      // e = 2j + b  <->  column col0 + 16j + 8b
-              const int n = col0 + 16 * (e >> 1) + 8 * (e & 1);
-              const T sv = sc[(size_t)g * p.N + scale_pos(n, grouped)];
-              const uint32_t s16 = *reinterpret_cast<const uint16_t*>(&sv);
+            for (int e = 0; e < 8; ++e) {
+              const uint32_t s16 = (sw[e >> 1] >> (16 * (e & 1))) & 0xffffu;
               s2[nb][e] = s16 | (s16 << 16);
-              if (HAS_ZP) {
-                const int nib = ((e & 1) << 2) | (e >> 1);
-                off2[nb][e] = DQ<T>::offset((int)((zword >> (4 * nib)) & 0xFu));
-              }
+              if (HAS_ZP) off2[nb][e] = DQ<T>::offset((int)((zword >> (4 * (((e & 1) << 2) | (e >> 1)))) & 0xFu));
             }
           }
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&pk_empty[ps]);
 
         const int s = c % MG_STAGES;
         mbar_wait(&empty[s], ((uint32_t)(c / MG_STAGES) & 1u) ^ 1u);   // stage's previous MMAs retired
-        uint8_t* wt = w_s + (size_t)s * MG_W_BYTES;
+        const uint32_t wt = w_addr + (uint32_t)s * MG_W_BYTES;
         const uint32_t a0 = (uint32_t)(((2 * dq) ^ cq) << 4) + 4u * m;       // k = 16dq + 2m (+1)
         const uint32_t a1 = (uint32_t)(((2 * dq + 1) ^ cq) << 4) + 4u * m;   // k = 16dq + 8 + 2m (+1)
 #pragma unroll
@@ -312,16 +366,16 @@ marlin_w4a16_tc5_kernel(const __grid_constant__ CUtensorMap tmap_a, const Marlin
             for (int j = 0; j < 4; ++j) {
               const uint32_t w = wq[j];
               const int row0 = nb * 64 + 16 * j + cq;
-              uint8_t* r0 = wt + row0 * 128;
-              uint8_t* r1 = r0 + 8 * 128;
+              const uint32_t r0 = wt + row0 * 128;
+              const uint32_t r1 = r0 + 8 * 128;
               const uint32_t x00 = lop3_and_or(w, 0x000f000fu, DQ<T>::MAGIC);
               const uint32_t x01 = lop3_and_or(w >> 4, 0x000f000fu, DQ<T>::MAGIC);
               const uint32_t x10 = lop3_and_or(w >> 8, 0x000f000fu, DQ<T>::MAGIC);
               const uint32_t x11 = lop3_and_or(w >> 12, 0x000f000fu, DQ<T>::MAGIC);
-              *reinterpret_cast<uint32_t*>(r0 + a0) = DQ<T>::sub_mul(x00, off2[nb][2 * j], s2[nb][2 * j]);
-              *reinterpret_cast<uint32_t*>(r0 + a1) = DQ<T>::sub_mul(x01, off2[nb][2 * j], s2[nb][2 * j]);
-              *reinterpret_cast<uint32_t*>(r1 + a0) = DQ<T>::sub_mul(x10, off2[nb][2 * j + 1], s2[nb][2 * j + 1]);
-              *reinterpret_cast<uint32_t*>(r1 + a1) = DQ<T>::sub_mul(x11, off2[nb][2 * j + 1], s2[nb][2 * j + 1]);
+              sts32(r0 + a0, DQ<T>::sub_mul(x00, off2[nb][2 * j], s2[nb][2 * j]));
+              sts32(r0 + a1, DQ<T>::sub_mul(x01, off2[nb][2 * j], s2[nb][2 * j]));
+              sts32(r1 + a0, DQ<T>::sub_mul(x10, off2[nb][2 * j + 1], s2[nb][2 * j + 1]));
+              sts32(r1 + a1, DQ<T>::sub_mul(x11, off2[nb][2 * j + 1], s2[nb][2 * j + 1]));
             }
           }
         }
@@ -337,7 +391,9 @@ marlin_w4a16_tc5_kernel(const __grid_constant__ CUtensorMap tmap_a, const Marlin
       const int ch = n_base + quad * 32 + lane;
       const bool ch_ok = ch < p.N;
       T* cptr = reinterpret_cast<T*>(p.c);
-      for (int col0 = 0; col0 < n_mma; col0 += 32) {
+      // the MG_TEAMS warps that share a lane quadrant interleave 32-column slabs
+      float* slab = p.split_k > 1 ? p.c_tmp + (size_t)blockIdx.z * p.M * p.N : nullptr;
+      for (int col0 = team * 32; col0 < n_mma; col0 += 32 * MG_TEAMS) {
         uint32_t v[32];
         tmem_ld32(tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)col0, v);
         if (ch_ok) {
@@ -346,10 +402,32 @@ marlin_w4a16_tc5_kernel(const __grid_constant__ CUtensorMap tmap_a, const Marlin
             const int tok = tok_base + col0 + t;
             if (col0 + t < toks) {
               const float f = __uint_as_float(v[t]);
-              if (p.split_k > 1) atomicAdd(p.c_tmp + (size_t)tok * p.N + ch, f);
+              if (slab != nullptr) slab[(size_t)tok * p.N + ch] = f;
               else cptr[(size_t)tok * p.N + ch] = from_f32<T>(f);
             }
           }
+        }
+      }
+      if (slab != nullptr) {
+        // split-k: every split stores its fp32 partial in its own slab; the LAST split to arrive on this
+        // tile's lock sums the slabs in a fixed order (deterministic, no atomics on data, no memset) and
+        // writes C, then returns the lock to zero — the reference's workspace contract.
+        __threadfence();
+        asm volatile("bar.sync 1, %0;" ::"n"(4 * MG_TEAMS * 32) : "memory");
+        const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+        if (threadIdx.x == 96) *tmem_slot = (atomicAdd(p.locks + tile, 1) == p.split_k - 1) ? 1u : 0u;
+        asm volatile("bar.sync 1, %0;" ::"n"(4 * MG_TEAMS * 32) : "memory");
+        if (*tmem_slot != 0u) {
+          __threadfence();
+          if (ch_ok) {
+            for (int t = team; t < toks; t += MG_TEAMS) {
+              const size_t off = (size_t)(tok_base + t) * p.N + ch;
+              float acc = 0.f;
+              for (int z = 0; z < p.split_k; ++z) acc += __ldcg(p.c_tmp + (size_t)z * p.M * p.N + off);
+              cptr[off] = from_f32<T>(acc);
+            }
+          }
+          if (threadIdx.x == 96) p.locks[tile] = 0;
         }
       }
       tc_fence_before();
@@ -360,13 +438,6 @@ marlin_w4a16_tc5_kernel(const __grid_constant__ CUtensorMap tmap_a, const Marlin
     tc_fence_after();
     tmem_dealloc(tmem_d, tmem_cols);
   }
-}
-
-template <typename T>
-__global__ void __launch_bounds__(256)
-splitk_convert_kernel(T* __restrict__ c, const float* __restrict__ c_tmp, int64_t numel) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += (int64_t)gridDim.x * blockDim.x)
-    c[i] = from_f32<T>(c_tmp[i]);
 }
 
 // ---- host -----------------------------------------------------------------------------------------
@@ -391,6 +462,7 @@ static int plan_split_k(int M, int N, int K, int group_size) {
   const int chunks = K / MG_KC;
   int split = 1;
   const int sms = num_sms();
+  if ((M + MG_TOK - 1) / MG_TOK > 32) return 1;   // lock workspace (N/64*16 ints) covers <= 32 token blocks
   while (tiles * split * 2 <= sms && chunks / (split * 2) >= 8) split *= 2;
   // keep every split on a group boundary
   const int gchunks = group_size > MG_KC ? group_size / MG_KC : 1;
@@ -424,22 +496,28 @@ extern "C" int b200_marlin_gemm_plan(int size_m, int size_n, int size_k, int num
 }
 
 extern "C" int b200_gptq_marlin_gemm(const void* a, const void* b_q_weight, const void* b_scales,
-                                     const void* b_zeros, void* c, float* c_tmp, int size_m, int size_n,
-                                     int size_k, int num_groups, int num_bits, int has_zp, int dtype,
-                                     int split_k, void* stream) {
+                                     const void* b_zeros, void* c, float* c_tmp, int32_t* workspace,
+                                     int size_m, int size_n, int size_k, int num_groups, int num_bits,
+                                     int has_zp, int dtype, int split_k, void* stream) {
   B200_CHECK(dtype == B200_F16 || dtype == B200_BF16, "gpt_marlin_gemm only supports bfloat16 and float16");
   B200_CHECK(num_bits == 4, "b200 marlin gemm: only 4-bit weights (uint4b8 / uint4) are implemented");
   B200_CHECK(size_n % 64 == 0, "size_n = " + std::to_string(size_n) + ", is not divisible by min_thread_n = 64");
   B200_CHECK(size_k % MG_KC == 0, "size_k = " + std::to_string(size_k) + " is not divisible by 64");
   B200_CHECK(num_groups >= 1 && size_k % num_groups == 0, "size_k is not divisible by the number of scale groups");
   const int gs = num_groups > 1 ? size_k / num_groups : -1;
-  B200_CHECK(gs == -1 || gs % 16 == 0, "unsupported group size " + std::to_string(gs));
+  B200_CHECK(gs == -1 || gs == size_k || gs == 32 || (gs % 64 == 0), "unsupported group size " + std::to_string(gs) +
+             " (supported: -1 / 32 / multiples of 64)");
   B200_CHECK(!has_zp || b_zeros != nullptr, "has_zp requires b_zeros");
   B200_CHECK((reinterpret_cast<uintptr_t>(a) & 15) == 0 && (reinterpret_cast<uintptr_t>(b_q_weight) & 15) == 0,
              "a and b_q_weight must be 16-byte aligned");
   if (size_m == 0) return 0;
   if (split_k <= 0) split_k = plan_split_k(size_m, size_n, size_k, gs);
-  B200_CHECK(split_k == 1 || c_tmp != nullptr, "split-k needs the zero-initialised fp32 reduce buffer");
+  B200_CHECK(split_k == 1 || (c_tmp != nullptr && workspace != nullptr),
+             "split-k needs the fp32 partial buffer [split_k, M, N] and the zeroed lock workspace");
+  {
+    const int chunks_total = size_k / MG_KC;
+    while (split_k > 1 && (split_k - 1) * ((chunks_total + split_k - 1) / split_k) >= chunks_total) --split_k;
+  }
   EncodeTiledFn enc = get_encode();
   B200_CHECK(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
 
@@ -458,9 +536,12 @@ extern "C" int b200_gptq_marlin_gemm(const void* a, const void* b_q_weight, cons
 
   MarlinParams p{};
   p.b_q = (const uint32_t*)b_q_weight; p.scales = b_scales; p.zeros = (const uint32_t*)b_zeros;
-  p.c = c; p.c_tmp = c_tmp; p.M = size_m; p.N = size_n; p.K = size_k; p.group_size = gs;
+  p.c = c; p.c_tmp = c_tmp; p.locks = workspace; p.M = size_m; p.N = size_n; p.K = size_k; p.group_size = gs;
   p.split_k = split_k;
   p.box_rows = box_rows;
+  p.grouped = (gs > 0 && gs < size_k) ? 1 : 0;
+  p.rows_per_chunk = (gs > 0 && gs < MG_KC) ? MG_KC / gs : 1;
+  p.chunks_per_group = (gs > MG_KC) ? gs / MG_KC : 1;
   const int chunks = size_k / MG_KC;
   p.chunks_per_split = (chunks + split_k - 1) / split_k;
   cudaStream_t st = (cudaStream_t)stream;
@@ -469,15 +550,5 @@ extern "C" int b200_gptq_marlin_gemm(const void* a, const void* b_q_weight, cons
     rc = has_zp ? launch_marlin<__nv_bfloat16, true>(tmap, p, st) : launch_marlin<__nv_bfloat16, false>(tmap, p, st);
   else
     rc = has_zp ? launch_marlin<__half, true>(tmap, p, st) : launch_marlin<__half, false>(tmap, p, st);
-  if (rc != 0) return rc;
-  if (split_k > 1) {
-    const int64_t numel = (int64_t)size_m * size_n;
-    int blocks = (int)((numel + 255) / 256 < (int64_t)num_sms() * 8 ? (numel + 255) / 256 : (int64_t)num_sms() * 8);
-    if (dtype == B200_BF16)
-      splitk_convert_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((__nv_bfloat16*)c, c_tmp, numel);
-    else
-      splitk_convert_kernel<__half><<<blocks, 256, 0, st>>>((__half*)c, c_tmp, numel);
-    return check_launch("splitk_convert_kernel");
-  }
-  return 0;
+  return rc;
 }

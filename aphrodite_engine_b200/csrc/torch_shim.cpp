@@ -325,14 +325,15 @@ torch::Tensor gptq_marlin_gemm_impl(torch::Tensor& a, torch::Tensor& b_q_weight,
   const int split = b200_marlin_gemm_plan((int)size_m, (int)size_n, (int)size_k, (int)num_groups);
   torch::Tensor c_tmp;
   float* c_tmp_ptr = nullptr;
-  if (split > 1) {  // the reference's fp32 global-reduce buffer (gptq_marlin.cu:2317-2327), zeroed here
-    c_tmp = torch::zeros({size_m, size_n}, a.options().dtype(at::kFloat));
+  if (split > 1) {  // the reference's fp32 global-reduce buffer (gptq_marlin.cu:2317-2327): one slab per split
+    c_tmp = torch::empty({split, size_m, size_n}, a.options().dtype(at::kFloat));
     c_tmp_ptr = c_tmp.data_ptr<float>();
   }
+  TORCH_CHECK(workspace.scalar_type() == at::kInt, "workspace must be int32");
   (void)use_fp32_reduce; (void)is_k_full;
   check(b200_gptq_marlin_gemm(a.data_ptr(), b_q_weight.data_ptr(), b_scales.data_ptr(),
-                              has_zp ? b_zeros.data_ptr() : nullptr, c.data_ptr(), c_tmp_ptr, (int)size_m,
-                              (int)size_n, (int)size_k, (int)num_groups, (int)type_bits, has_zp ? 1 : 0,
+                              has_zp ? b_zeros.data_ptr() : nullptr, c.data_ptr(), c_tmp_ptr,
+                              workspace.data_ptr<int>(), (int)size_m, (int)size_n, (int)size_k, (int)num_groups, (int)type_bits, has_zp ? 1 : 0,
                               dtype_code(a, "gptq_marlin_gemm"), split, cur_stream()));
   return c;
 }

@@ -156,14 +156,16 @@ int b200_activation(void* out, const void* input, int num_tokens, int d, int act
  * a [size_m, size_k] f16/bf16 contiguous; b_q_weight int32 [size_k/16, size_n*16/pack] (Marlin tiles);
  * b_scales [num_groups, size_n] (Marlin-permuted, num_groups == 1: channel-wise); b_zeros int32
  * [num_groups, size_n/8] (AWQ integer zero points, Marlin layout) or NULL; c [size_m, size_n].
- * c_tmp: fp32 [size_m, size_n], ZERO-INITIALISED, needed only when the plan splits k
- * (b200_marlin_gemm_plan(...) > 1; the reference's use_fp32_reduce buffer, gptq_marlin.cu:2313-2327).
- * split_k <= 0 = use the plan. 4-bit only (uint4b8, uint4+zp); act-order (g_idx/perm) is not supported. */
+ * Split-k (b200_marlin_gemm_plan(...) > 1) needs c_tmp: fp32 [split_k, size_m, size_n] scratch (no
+ * initialisation; the reference's use_fp32_reduce buffer, gptq_marlin.cu:2313-2327) and `workspace`:
+ * int32 [>= size_n/64*16], ZERO on entry and returned to zero (the reference's lock workspace,
+ * torch_bindings.cpp:167-176). The last split to arrive sums the partial slabs in a fixed order
+ * (deterministic). split_k <= 0 = use the plan. 4-bit only (uint4b8, uint4+zp); act-order (g_idx/perm) is not supported. */
 int b200_marlin_gemm_plan(int size_m, int size_n, int size_k, int num_groups);
 int b200_gptq_marlin_gemm(const void* a, const void* b_q_weight, const void* b_scales,
-                          const void* b_zeros, void* c, float* c_tmp, int size_m, int size_n,
-                          int size_k, int num_groups, int num_bits, int has_zp, int dtype,
-                          int split_k, void* stream);
+                          const void* b_zeros, void* c, float* c_tmp, int32_t* workspace,
+                          int size_m, int size_n, int size_k, int num_groups, int num_bits,
+                          int has_zp, int dtype, int split_k, void* stream);
 /* b_q_weight: GPTQ int32 [size_k/pack, size_n]; perm: int32 [size_k] act-order sort indices or NULL;
  * out: int32 [size_k/16, size_n*16/pack]. Bit-exact integer re-tiling. num_bits 4 or 8. */
 int b200_gptq_marlin_repack(const void* b_q_weight, const int32_t* perm, void* out, int size_k,

@@ -89,6 +89,20 @@ REF_SCHEMAS = {
         " Tensor slot_mapping, str kv_cache_dtype, float k_scale, float v_scale) -> ()",
     "_C_cache_ops::convert_fp8":
         "convert_fp8(Tensor! dst_cache, Tensor src_cache, float scale, str kv_cache_dtype) -> ()",
+    "_C::gptq_marlin_gemm":
+        "gptq_marlin_gemm(Tensor a, Tensor b_q_weight, Tensor b_scales, Tensor b_zeros, Tensor g_idx, Tensor perm,"
+        " Tensor workspace, __torch__.torch.classes._core_C.ScalarType b_q_type, int size_m, int size_n,"
+        " int size_k, bool is_k_full, bool has_zp, bool use_fp32_reduce, bool is_zp_float) -> Tensor",
+    "_C::gptq_marlin_repack":
+        "gptq_marlin_repack(Tensor b_q_weight, Tensor perm, SymInt size_k, SymInt size_n, int num_bits) -> Tensor",
+    "_C::awq_marlin_repack":
+        "awq_marlin_repack(Tensor b_q_weight, SymInt size_k, SymInt size_n, int num_bits) -> Tensor",
+    "_C::moe_align_block_size":
+        "moe_align_block_size(Tensor topk_ids, int num_experts, int block_size, Tensor! sorted_token_ids,"
+        " Tensor! experts_ids, Tensor! num_tokens_post_pad) -> ()",
+    "_moe_C::topk_softmax":
+        "topk_softmax(Tensor! topk_weights, Tensor! topk_indices, Tensor! token_expert_indices,"
+        " Tensor gating_output) -> ()",
     "_C_cuda_utils::get_device_attribute": "get_device_attribute(int attribute, int device_id) -> int",
     "_C_cuda_utils::get_max_shared_memory_per_block_device_attribute":
         "get_max_shared_memory_per_block_device_attribute(int device_id) -> int",
@@ -115,6 +129,20 @@ def test_shim_exports_pyinit_for_import_as_aphrodite_C():
     from aphrodite_engine_b200 import _native
     lib = ctypes.CDLL(_native.SHIM_PATH)
     assert hasattr(lib, "PyInit__C")
+    assert hasattr(ctypes.CDLL(_native.MOE_PATH), "PyInit__moe_C")
+    assert hasattr(ctypes.CDLL(_native.CORE_PATH), "PyInit__core_C")
+
+
+def test_scalar_type_class_mirrors_reference_interface():
+    from aphrodite_engine_b200.scalar_type import ScalarType, scalar_types as st
+    assert (st.uint4b8.size_bits, st.uint4b8.bias, st.uint4b8.min(), st.uint4b8.max()) == (4, 8, -8, 7)
+    assert (st.uint4.min(), st.uint4.max(), st.uint8b128.min(), st.uint8b128.max()) == (0, 15, -128, 127)
+    assert st.int8.min() == -128 and st.int8.max() == 127 and st.int8.is_signed()
+    assert st.uint4b8.is_integer() and not st.uint4b8.is_floating_point() and st.uint4b8.has_bias()
+    assert str(st.uint4b8) == "uint4b8" and repr(st.uint4) == "ScalarType.uint4"
+    assert st.float16_e5m10.max() == 65504.0 and st.float16_e5m10.is_ieee_754()
+    assert st.uint4b8 == ScalarType.uint(4, 8) and not (st.uint4b8 == st.uint4)
+    assert ScalarType(0, 4, 8, False) == st.uint4b8
 
 
 def test_product_package_never_imports_the_oracle():

@@ -104,10 +104,14 @@ def test_gemm_llama_shapes_split_k(ops, cabi):
         w = torch.randn(K, N).to(torch.bfloat16)
         w_ref, mq, ms = om.marlin_quantize(w, 4, 128)
         empty = torch.empty(0, dtype=torch.int32, device=DEV)
-        out = ops.gptq_marlin_gemm(a.to(DEV), mq.to(DEV), ms.to(DEV), empty, empty, empty, _workspace(N),
-                                   _types().uint4b8, M, N, K, True, False, True, False)
+        ws = _workspace(N)
+        outs = [ops.gptq_marlin_gemm(a.to(DEV), mq.to(DEV), ms.to(DEV), empty, empty, empty, ws,
+                                     _types().uint4b8, M, N, K, True, False, True, False) for _ in range(3)]
         torch.cuda.synchronize()
-        _check_gemm(out, om.marlin_gemm(a, w_ref))
+        _check_gemm(outs[0], om.marlin_gemm(a, w_ref))
+        assert (ws == 0).all(), "the lock workspace must be returned to zero"
+        assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2]), "split-k reduce must be deterministic"
+        assert cabi.b200_marlin_gemm_plan(M, N, K, K // 128) >= 1
 
 
 def test_marlin_argument_errors(ops):
