@@ -27,6 +27,7 @@
 
 #include <cuda.h>
 
+#include <stdlib.h>
 #include <type_traits>
 
 namespace b200 {
@@ -34,22 +35,18 @@ namespace b200 {
 static constexpr int MG_NT = 128;        // output channels per CTA  (UMMA M)
 static constexpr int MG_KC = 64;         // k per stage (one 128-byte swizzle row of 16-bit elements)
 static constexpr int MG_TOK = 256;       // max tokens per CTA       (UMMA N)
-static constexpr int MG_STAGES = 3;      // (activation tile + dequantised weight tile) stages
-static constexpr int MG_PK_STAGES = 8;   // packed-weight ring
-static constexpr int MG_TEAMS = 2;        // dequant teams (4 warps each) working on alternate chunks
-static constexpr int MG_THREADS = (3 + 4 * MG_TEAMS) * 32;
-static constexpr int MG_ACT_BYTES = MG_TOK * 128;  // 32 KB
-static constexpr int MG_W_BYTES = MG_NT * 128;     // 16 KB
-static constexpr int MG_PK_W_BYTES = 4 * 256 * 4;  // 4 k-tiles x 256 words of packed weights
-// every packed stage also carries the chunk's scale rows (<= 2 groups x 128 channels x 2 B) and zero-point
-// rows (<= 2 x 16 words), copied by the same producer on the same mbarrier: no global-load latency in the
-// dequant loop
-static constexpr int MG_PK_SC_OFF = MG_PK_W_BYTES;         // 2 x 256 B
-static constexpr int MG_PK_ZP_OFF = MG_PK_SC_OFF + 512;    // 2 x 64 B
-static constexpr int MG_PK_BYTES = MG_PK_ZP_OFF + 128;     // 4736 B (multiple of 64)
-static_assert(MG_PK_STAGES % MG_TEAMS == 0, "a packed stage must always be consumed by the same team");
-static constexpr int MG_SMEM = MG_STAGES * (MG_ACT_BYTES + MG_W_BYTES) + MG_PK_STAGES * MG_PK_BYTES +
-                               512 /*barriers*/ + 1024 /*alignment slack*/;
+static constexpr int MG_MAX_STAGES = 8;  // (activation tile + dequantised weight tile) stages: 3 at 256 tokens, more below
+static constexpr int MG_TEAMS = 4;       // dequant teams (4 warps each) working on interleaved chunks (TLP for the ALU chains)
+static constexpr int MG_DQ_WARPS = 4 * MG_TEAMS;
+static constexpr int MG_WARP_TMA = MG_DQ_WARPS;       // highest warp ids = highest issue priority
+static constexpr int MG_WARP_MMA = MG_DQ_WARPS + 1;
+static constexpr int MG_THREADS = (MG_DQ_WARPS + 2) * 32;
+static constexpr int MG_W_BYTES = MG_NT * 128;        // 16 KB dequantised weight tile
+// per-warp cp.async ring slot: 2 x 512 B packed words | 2 x 512 B scale vectors | 2 x 128 B zero points
+static constexpr int MG_SLOT_BYTES = 2304;
+static constexpr int MG_RING_DEPTH = 2;               // chunks in flight per warp (x 4 teams = 8 chunks ahead)
+static constexpr int MG_SMEM_TOTAL = 226 * 1024;      // opt-in dynamic shared memory available to one CTA
+static constexpr int MG_SMEM_FIXED = MG_DQ_WARPS * MG_RING_DEPTH * MG_SLOT_BYTES + 1024 /*barriers*/ + 1024 /*align*/;
 
 struct MarlinParams {
   const uint32_t* b_q;   // [K/16, N*2] int32, Marlin layout
@@ -66,6 +63,9 @@ struct MarlinParams {
   int grouped;           // 1: b_scales has one row per k-group (Marlin "grouped" permutation), 0: single row
   int rows_per_chunk;    // scale rows a 64-wide chunk spans (1, or 2 when group_size == 32)
   int chunks_per_group;  // 64-wide chunks per scale group (>= 1)
+  int stages;            // act/weight pipeline depth (2..8), chosen from the token count
+  int act_bytes;         // bytes of one activation stage (box_rows * 128, rounded up to 1024)
+  int debug;             // B200_MARLIN_DEBUG (timing experiments only): 1 skip dequant math, 2 skip MMAs, 4 skip act TMA
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
@@ -129,8 +129,28 @@ __device__ __forceinline__ uint32_t lds32(uint32_t a) {
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
   return v;
 }
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void* g) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t saddr, const void* g) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
 __device__ __forceinline__ void sts32(uint32_t a, uint32_t v) {
   asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+
+// debug-only cycle attribution (B200_MARLIN_DEBUG & 16): CTA (0,0,0) accumulates, per role, the cycles spent
+// in each mbarrier wait; read back with b200_debug_marlin_prof()
+__device__ unsigned long long g_mg_prof[32];
+__device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, bool prof, unsigned long long& acc) {
+  if (!prof) { mbar_wait(bar, parity); return; }
+  const long long t0 = clock64();
+  mbar_wait(bar, parity);
+  acc += (unsigned long long)(clock64() - t0);
 }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
@@ -185,16 +205,18 @@ __global__ void __launch_bounds__(MG_THREADS, 1)
 marlin_w4a16_tc5_kernel(const __grid_constant__ CUtensorMap tmap_a, const MarlinParams p) {
   extern __shared__ uint8_t mg_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(mg_smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* act_s = smem;                                       // [STAGES][256 x 128 B]
-  uint8_t* w_s = act_s + MG_STAGES * MG_ACT_BYTES;             // [STAGES][128 x 128 B]
-  uint8_t* pk_s = w_s + MG_STAGES * MG_W_BYTES;                // [PK_STAGES][4 KB]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(pk_s + MG_PK_STAGES * MG_PK_BYTES);
-  uint64_t* full_act = bars;                       // [STAGES]  TMA tx
-  uint64_t* full_w = full_act + MG_STAGES;         // [STAGES]  4 dequant warps
-  uint64_t* empty = full_w + MG_STAGES;            // [STAGES]  tcgen05.commit
-  uint64_t* pk_full = empty + MG_STAGES;           // [PK_STAGES]
-  uint64_t* pk_empty = pk_full + MG_PK_STAGES;     // [PK_STAGES] 4 dequant warps
-  uint64_t* accum_full = pk_empty + MG_PK_STAGES;  // [1]
+  const int NS = p.stages;
+  uint8_t* act_s = smem;                                       // [NS][box_rows x 128 B]   (TMA, SWIZZLE_128B)
+  uint8_t* w_s = act_s + (size_t)NS * p.act_bytes;             // [NS][128 x 128 B]        (dequantised weights)
+  uint8_t* ring_s = w_s + (size_t)NS * MG_W_BYTES;             // [DQ_WARPS][DEPTH][slot]  (per-warp cp.async rings)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring_s + (size_t)MG_DQ_WARPS * MG_RING_DEPTH * MG_SLOT_BYTES);
+  uint64_t* full_act = bars;                        // [NS]  TMA tx
+  uint64_t* full_w = full_act + MG_MAX_STAGES;      // [NS]  4 dequant warps of one team
+  // "stage free" barriers, TWO per stage used alternately (use u of a stage signals empty[(u&1)][s]): a waiter
+  // is then never two phases ahead of the barrier it tests, whatever the team / stage counts (a parity test
+  // two phases ahead passes vacuously — the bug class of the attention ring)
+  uint64_t* empty = full_w + MG_MAX_STAGES;         // [2][NS]  tcgen05.commit
+  uint64_t* accum_full = empty + 2 * MG_MAX_STAGES; // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -210,231 +232,253 @@ marlin_w4a16_tc5_kernel(const __grid_constant__ CUtensorMap tmap_a, const Marlin
   while ((int)tmem_cols < n_mma) tmem_cols <<= 1;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < MG_STAGES; ++i) {
+    for (int i = 0; i < MG_MAX_STAGES; ++i) {
       mbar_init(&full_act[i], 1);
       mbar_init(&full_w[i], 4);
       mbar_init(&empty[i], 1);
-    }
-    for (int i = 0; i < MG_PK_STAGES; ++i) {
-      mbar_init(&pk_full[i], 1);
-      mbar_init(&pk_empty[i], 4);
+      mbar_init(&empty[MG_MAX_STAGES + i], 1);
     }
     mbar_init(accum_full, 1);
     fence_mbar_init();
   }
-  if (warp == 0) tmem_alloc(tmem_slot, tmem_cols);
+  if (warp == MG_WARP_TMA) tmem_alloc(tmem_slot, tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = *tmem_slot;
+  const bool prof = (p.debug & 16) && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+  unsigned long long w0 = 0, w1 = 0;
+  const long long t_role0 = clock64();
 
-  if (nchunks > 0) {
-    if (warp == 0) {
-      // ===================== activation TMA producer =====================
-      if (lane == 0) {
-        for (int c = 0; c < nchunks; ++c) {
-          const int s = c % MG_STAGES;
-          const uint32_t use = (uint32_t)(c / MG_STAGES);
-          mbar_wait(&empty[s], (use & 1u) ^ 1u);
-          mbar_arrive_expect_tx(&full_act[s], (uint32_t)p.box_rows * 128u);  // TMA always moves the full box
-          tma_load_2d(act_s + (size_t)s * MG_ACT_BYTES, &tmap_a, &full_act[s], (chunk0 + c) * MG_KC, tok_base);
+  // Warp roles. The two single-thread roles sit in the HIGHEST warp ids: the issue arbiter favours high warp
+  // ids, and with the ALU-heavy dequant warps above them the TMA / MMA issuers were starved (measured:
+  // 500-1200 cycles per issued TMA / 200 per MMA).
+  if (nchunks > 0 && warp == MG_WARP_TMA) {
+    // ===================== activation TMA producer =====================
+    if (lane == 0) {
+      for (int c = 0; c < nchunks; ++c) {
+        const int s = c % NS;
+        const uint32_t use = (uint32_t)(c / NS);
+        if (use > 0) mbar_wait_t(&empty[((use - 1) & 1u) * MG_MAX_STAGES + s], ((use - 1) >> 1) & 1u, prof, w0);
+        if (p.debug & 4) { mbar_arrive(&full_act[s]); continue; }
+        mbar_arrive_expect_tx(&full_act[s], (uint32_t)p.box_rows * 128u);  // TMA always moves the full box
+        tma_load_2d(act_s + (size_t)s * p.act_bytes, &tmap_a, &full_act[s], (chunk0 + c) * MG_KC, tok_base);
+      }
+      if (prof) { g_mg_prof[0] = (unsigned long long)(clock64() - t_role0); g_mg_prof[1] = w0; g_mg_prof[2] = (unsigned long long)nchunks; }
+    }
+  } else if (nchunks > 0 && warp == MG_WARP_MMA) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A/B = T, both K-major, N, M = 128
+      const uint32_t fmt = std::is_same<T, __nv_bfloat16>::value ? 1u : 0u;   // 0 = F16, 1 = BF16
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n_mma >> 3) << 17) |
+                             ((uint32_t)(MG_NT >> 4) << 24);
+      for (int c = 0; c < nchunks; ++c) {
+        const int s = c % NS;
+        const uint32_t par = (uint32_t)(c / NS) & 1u;
+        mbar_wait_t(&full_act[s], par, prof, w0);
+        mbar_wait_t(&full_w[s], par, prof, w1);
+        tc_fence_after();
+        const uint64_t a_desc = make_sw128_desc(smem_u32(w_s + (size_t)s * MG_W_BYTES));
+        const uint64_t b_desc = make_sw128_desc(smem_u32(act_s + (size_t)s * p.act_bytes));
+#pragma unroll
+        for (int ks = 0; ks < MG_KC / 16; ++ks) {
+          if (p.debug & 2) break;
+          // advancing 16 k = 32 bytes inside the 128-byte swizzle row = +2 in the descriptor's (addr >> 4) field
+          umma_f16(tmem_d, a_desc + (uint64_t)(2 * ks), b_desc + (uint64_t)(2 * ks), idesc, (c > 0 || ks > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty[((uint32_t)(c / NS) & 1u) * MG_MAX_STAGES + s]);   // frees act/w stage s when these MMAs retire
+      }
+      umma_commit(accum_full);                   // accumulator complete
+      if (prof) { g_mg_prof[4] = (unsigned long long)(clock64() - t_role0); g_mg_prof[5] = w0; g_mg_prof[6] = w1; }
+    }
+  } else if (nchunks > 0 && warp < MG_DQ_WARPS) {
+    // ===================== dequant warps =====================
+    // team = warp / 4 takes chunks team, team + TEAMS, ...; inside a team warp dq = warp % 4 owns k-tile dq of
+    // the chunk. Every warp streams ITS OWN packed words, scale vectors and zero points with cp.async
+    // (LDGSTS, 16 B per lane) into a private 4-deep ring: no producer warp, no TMA-unit time (the unit costs
+    // ~400 cycles per operation and was the bottleneck when weights came by TMA / bulk copies), no barriers —
+    // each lane reads back exactly the bytes it fetched.
+    const int team = warp >> 2;
+    const int dq = warp & 3;
+    const int m = lane & 3, cq = lane >> 2;
+    const bool grouped = p.grouped != 0;
+    const T* sc = reinterpret_cast<const T*>(p.scales);
+    uint32_t s2[2][8];    // per Marlin block: scale pairs {s,s} for column (j, b) at index 2j+b
+    uint32_t off2[2][8];  // per column: 16-bit pair of MAGIC + (8 | zero point)
+#pragma unroll
+    for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { s2[nb][e] = 0; off2[nb][e] = DQ<T>::offset(8); }
+    if (!grouped) {
+      // channel-wise: one scale row (and zero-point row) for the whole k range, read once
+      for (int nb = 0; nb < nblk; ++nb) {
+        const int col0 = n_base + nb * 64 + cq;
+        uint32_t zword = 0;
+        if (HAS_ZP) zword = p.zeros[(n_base + nb * 64) / 8 + cq];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {      // e = 2j + b  <->  column col0 + 16j + 8b
+          const int n = col0 + 16 * (e >> 1) + 8 * (e & 1);
+          const T sv = sc[scale_pos(n, false)];
+          const uint32_t s16 = *reinterpret_cast<const uint16_t*>(&sv);
+          s2[nb][e] = s16 | (s16 << 16);
+          if (HAS_ZP) off2[nb][e] = DQ<T>::offset((int)((zword >> (4 * (((e & 1) << 2) | (e >> 1)))) & 0xFu));
         }
       }
-    } else if (warp == 1) {
-      // ===================== MMA issuer =====================
-      if (lane == 0) {
-        // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A/B = T, both K-major, N, M = 128
-        const uint32_t fmt = std::is_same<T, __nv_bfloat16>::value ? 1u : 0u;   // 0 = F16, 1 = BF16
-        const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n_mma >> 3) << 17) |
-                               ((uint32_t)(MG_NT >> 4) << 24);
-        for (int c = 0; c < nchunks; ++c) {
-          const int s = c % MG_STAGES;
-          const uint32_t par = (uint32_t)(c / MG_STAGES) & 1u;
-          mbar_wait(&full_act[s], par);
-          mbar_wait(&full_w[s], par);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(w_s + (size_t)s * MG_W_BYTES);
-          const uint32_t b_addr = smem_u32(act_s + (size_t)s * MG_ACT_BYTES);
-#pragma unroll
-          for (int ks = 0; ks < MG_KC / 16; ++ks) {
-            umma_f16(tmem_d, make_sw128_desc(a_addr + ks * 32), make_sw128_desc(b_addr + ks * 32), idesc,
-                     (c > 0 || ks > 0) ? 1u : 0u);
+    }
+    const uint32_t ring = smem_u32(ring_s) + (uint32_t)warp * (MG_RING_DEPTH * MG_SLOT_BYTES) + (uint32_t)lane * 16u;
+    const uint32_t w_addr = smem_u32(w_s);
+    const int row_words = p.N * 2;                      // int32 per 16-row k-tile of the Marlin matrix
+    // global sources of this lane: words 4*lane..4*lane+3 of block nb, k-tile (4*chunk + dq)
+    const uint32_t* wsrc = p.b_q + (size_t)(n_base / 64) * 128 + (size_t)lane * 4;
+    auto prefetch = [&](int c) {       // issue this lane's cp.async for chunk c into its ring slot, one group
+      if (c < nchunks) {
+        const uint32_t slot = ring + (uint32_t)((c / MG_TEAMS) % MG_RING_DEPTH) * MG_SLOT_BYTES;
+        const uint32_t* src = wsrc + (size_t)((chunk0 + c) * 4 + dq) * row_words;
+        cp_async16(slot, src);
+        if (nblk > 1) cp_async16(slot + 512, src + 128);
+        if (grouped) {
+          const int g = p.rows_per_chunk == 2 ? (chunk0 + c) * 2 + (dq >> 1) : (chunk0 + c) / p.chunks_per_group;
+          const uint8_t* ssrc = reinterpret_cast<const uint8_t*>(p.scales) + ((size_t)g * p.N + n_base + 8 * cq) * 2;
+          cp_async16(slot + 1024, ssrc);
+          if (nblk > 1) cp_async16(slot + 1536, ssrc + 128);
+          if (HAS_ZP) {
+            const uint32_t* zsrc = p.zeros + (size_t)g * (p.N / 8) + n_base / 8 + cq;
+            cp_async4(slot + 2048 - (uint32_t)lane * 12u, zsrc);            // 4-byte slots: lane * 4
+            if (nblk > 1) cp_async4(slot + 2176 - (uint32_t)lane * 12u, zsrc + 8);
           }
-          umma_commit(&empty[s]);                  // frees act/w stage s when these MMAs retire
-        }
-        umma_commit(accum_full);                   // accumulator complete
-      }
-    } else if (warp == 2) {
-      // ===================== packed-weight producer =====================
-      if (lane == 0) {
-        const int row_words = p.N * 2;             // int32 per 16-row k-tile
-        const uint32_t bytes = (uint32_t)nblk * 512u;
-        for (int c = 0; c < nchunks; ++c) {
-          const int ps = c % MG_PK_STAGES;
-          const uint32_t use = (uint32_t)(c / MG_PK_STAGES);
-          mbar_wait(&pk_empty[ps], (use & 1u) ^ 1u);
-          const uint32_t sc_bytes = (uint32_t)nblk * 128u;          // 64 channels x 2 B per Marlin block
-          const uint32_t zp_bytes = (uint32_t)nblk * 32u;           // 8 int32 per Marlin block
-          const int srows = p.grouped ? p.rows_per_chunk : 0;       // channel-wise scales are read once
-          mbar_arrive_expect_tx(&pk_full[ps], 4u * bytes + (uint32_t)srows * (sc_bytes + (HAS_ZP ? zp_bytes : 0u)));
-          const uint32_t* src = p.b_q + (size_t)((chunk0 + c) * 4) * row_words + (size_t)(n_base / 64) * 128;
-          uint8_t* dst = pk_s + (size_t)ps * MG_PK_BYTES;
-#pragma unroll
-          for (int kt = 0; kt < 4; ++kt)
-            bulk_g2s_plain(dst + kt * 1024, src + (size_t)kt * row_words, bytes, &pk_full[ps]);
-          const int g0 = p.rows_per_chunk == 2 ? (chunk0 + c) * 2 : (chunk0 + c) / p.chunks_per_group;
-          for (int r = 0; r < srows; ++r) {
-            bulk_g2s_plain(dst + MG_PK_SC_OFF + r * 256,
-                           reinterpret_cast<const uint8_t*>(p.scales) + ((size_t)(g0 + r) * p.N + n_base) * 2,
-                           sc_bytes, &pk_full[ps]);
-            if (HAS_ZP)
-              bulk_g2s_plain(dst + MG_PK_ZP_OFF + r * 64, p.zeros + (size_t)(g0 + r) * (p.N / 8) + n_base / 8,
-                             zp_bytes, &pk_full[ps]);
-          }
         }
       }
-    } else {
-      // ===================== dequant warps: team `team` takes chunks team, team+TEAMS, ...; inside a
-      // team warp `dq` owns k-tile dq of the chunk. Two teams overlap one chunk's barrier / fence latency
-      // with the other's ALU work. (Each team's waits on a stage are chained through its own previous
-      // chunks, so no parity test can pass vacuously — see the attention kernel's ring invariant.)
-      const int team = (warp - 3) >> 2;
-      const int dq = (warp - 3) & 3;
-      const int m = lane & 3, cq = lane >> 2;
-      const bool grouped = p.group_size > 0 && p.group_size < p.K;
-      const T* sc = reinterpret_cast<const T*>(p.scales);
-      uint32_t s2[2][8];    // per Marlin block: scale pairs {s,s} for column (j, b) at index 2j+b
-      uint32_t off2[2][8];  // per column: 16-bit pair of MAGIC + (8 | zero point)
+      cp_async_commit();
+    };
 #pragma unroll
-      for (int nb = 0; nb < 2; ++nb)
-#pragma unroll
-        for (int e = 0; e < 8; ++e) { s2[nb][e] = 0; off2[nb][e] = DQ<T>::offset(8); }
-      if (!grouped) {
-        // channel-wise: one scale row (and zero-point row) for the whole k range, read once
+    for (int d = 0; d < MG_RING_DEPTH; ++d) prefetch(team + d * MG_TEAMS);
+
+    for (int c = team; c < nchunks; c += MG_TEAMS) {
+      cp_async_wait<MG_RING_DEPTH - 1>();           // this lane's copies for chunk c have landed
+      const uint32_t slot = ring + (uint32_t)((c / MG_TEAMS) % MG_RING_DEPTH) * MG_SLOT_BYTES;
+      uint4 q[2];
+      q[0] = lds128(slot);
+      q[1] = (nblk > 1) ? lds128(slot + 512) : make_uint4(0, 0, 0, 0);
+      if (grouped) {
+        // Marlin's grouped scale permutation puts this lane's 8 scales (columns 16j + 8b + cq of a block) in 16
+        // contiguous bytes at position 8*cq of the block's 64-entry row; the 8 zero points are one int32
         for (int nb = 0; nb < nblk; ++nb) {
-          const int col0 = n_base + nb * 64 + cq;
+          const uint4 sv = lds128(slot + 1024 + nb * 512);
+          const uint32_t sw[4] = {sv.x, sv.y, sv.z, sv.w};
           uint32_t zword = 0;
-          if (HAS_ZP) zword = p.zeros[(n_base + nb * 64) / 8 + cq];
+          if (HAS_ZP) zword = lds32(slot + 2048 + nb * 128 - (uint32_t)lane * 12u);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {      // e = 2j + b  <->  column col0 + 16j + 8b
-            const int n = col0 + 16 * (e >> 1) + 8 * (e & 1);
-            const T sv = sc[scale_pos(n, false)];
-            const uint32_t s16 = *reinterpret_cast<const uint16_t*>(&sv);
+          for (int e = 0; e < 8; ++e) {
+            const uint32_t s16 = (sw[e >> 1] >> (16 * (e & 1))) & 0xffffu;
             s2[nb][e] = s16 | (s16 << 16);
             if (HAS_ZP) off2[nb][e] = DQ<T>::offset((int)((zword >> (4 * (((e & 1) << 2) | (e >> 1)))) & 0xFu));
           }
         }
       }
-      const int my_row = p.rows_per_chunk == 2 ? (dq >> 1) : 0;   // group_size 32: k-tiles 0,1 | 2,3
-      const uint32_t pk_addr = smem_u32(pk_s), w_addr = smem_u32(w_s);
-      for (int c = team; c < nchunks; c += MG_TEAMS) {
-        const int ps = c % MG_PK_STAGES;
-        mbar_wait(&pk_full[ps], (uint32_t)(c / MG_PK_STAGES) & 1u);
-        const uint32_t stage = pk_addr + (uint32_t)ps * MG_PK_BYTES;
-        uint4 q[2];
-        q[0] = lds128(stage + dq * 1024 + lane * 16);
-        q[1] = (nblk > 1) ? lds128(stage + dq * 1024 + 512 + lane * 16) : make_uint4(0, 0, 0, 0);
-        if (grouped) {
-          // Marlin's grouped scale permutation puts this lane's 8 scales (columns 16j + 8b + cq of a block)
-          // in 16 contiguous bytes at position 8*cq of the block's 64-entry row; zero points: one int32
-          for (int nb = 0; nb < nblk; ++nb) {
-            const uint4 sv = lds128(stage + MG_PK_SC_OFF + my_row * 256 + nb * 128 + cq * 16);
-            const uint32_t sw[4] = {sv.x, sv.y, sv.z, sv.w};
-            uint32_t zword = 0;
-            if (HAS_ZP) zword = lds32(stage + MG_PK_ZP_OFF + my_row * 64 + nb * 32 + cq * 4);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const uint32_t s16 = (sw[e >> 1] >> (16 * (e & 1))) & 0xffffu;
-              s2[nb][e] = s16 | (s16 << 16);
-              if (HAS_ZP) off2[nb][e] = DQ<T>::offset((int)((zword >> (4 * (((e & 1) << 2) | (e >> 1)))) & 0xFu));
-            }
-          }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&pk_empty[ps]);
-
-        const int s = c % MG_STAGES;
-        mbar_wait(&empty[s], ((uint32_t)(c / MG_STAGES) & 1u) ^ 1u);   // stage's previous MMAs retired
-        const uint32_t wt = w_addr + (uint32_t)s * MG_W_BYTES;
-        const uint32_t a0 = (uint32_t)(((2 * dq) ^ cq) << 4) + 4u * m;       // k = 16dq + 2m (+1)
-        const uint32_t a1 = (uint32_t)(((2 * dq + 1) ^ cq) << 4) + 4u * m;   // k = 16dq + 8 + 2m (+1)
-#pragma unroll
-        for (int nb = 0; nb < 2; ++nb) {
-          if (nb < nblk) {
-            const uint32_t wq[4] = {q[nb].x, q[nb].y, q[nb].z, q[nb].w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint32_t w = wq[j];
-              const int row0 = nb * 64 + 16 * j + cq;
-              const uint32_t r0 = wt + row0 * 128;
-              const uint32_t r1 = r0 + 8 * 128;
-              const uint32_t x00 = lop3_and_or(w, 0x000f000fu, DQ<T>::MAGIC);
-              const uint32_t x01 = lop3_and_or(w >> 4, 0x000f000fu, DQ<T>::MAGIC);
-              const uint32_t x10 = lop3_and_or(w >> 8, 0x000f000fu, DQ<T>::MAGIC);
-              const uint32_t x11 = lop3_and_or(w >> 12, 0x000f000fu, DQ<T>::MAGIC);
-              sts32(r0 + a0, DQ<T>::sub_mul(x00, off2[nb][2 * j], s2[nb][2 * j]));
-              sts32(r0 + a1, DQ<T>::sub_mul(x01, off2[nb][2 * j], s2[nb][2 * j]));
-              sts32(r1 + a0, DQ<T>::sub_mul(x10, off2[nb][2 * j + 1], s2[nb][2 * j + 1]));
-              sts32(r1 + a1, DQ<T>::sub_mul(x11, off2[nb][2 * j + 1], s2[nb][2 * j + 1]));
-            }
-          }
-        }
-        fence_proxy_async();          // generic-proxy stores -> visible to the tensor core's async proxy
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&full_w[s]);
+      const int s = c % NS;
+      {
+        const uint32_t use = (uint32_t)(c / NS);          // stage's previous MMAs must have retired
+        if (use > 0) mbar_wait_t(&empty[((use - 1) & 1u) * MG_MAX_STAGES + s], ((use - 1) >> 1) & 1u, prof && warp == 0 && lane == 0, w1);
       }
-
-      // ===================== epilogue: TMEM -> C =====================
-      mbar_wait(accum_full, 0);
-      tc_fence_after();
-      const int quad = warp & 3;                            // TMEM lanes 32*quad .. +31 belong to this warp
-      const int ch = n_base + quad * 32 + lane;
-      const bool ch_ok = ch < p.N;
-      T* cptr = reinterpret_cast<T*>(p.c);
-      // the MG_TEAMS warps that share a lane quadrant interleave 32-column slabs
-      float* slab = p.split_k > 1 ? p.c_tmp + (size_t)blockIdx.z * p.M * p.N : nullptr;
-      for (int col0 = team * 32; col0 < n_mma; col0 += 32 * MG_TEAMS) {
-        uint32_t v[32];
-        tmem_ld32(tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)col0, v);
-        if (ch_ok) {
+      const uint32_t wt = w_addr + (uint32_t)s * MG_W_BYTES;
+      const uint32_t a0 = (uint32_t)(((2 * dq) ^ cq) << 4) + 4u * m;       // k = 16dq + 2m (+1)
+      const uint32_t a1 = (uint32_t)(((2 * dq + 1) ^ cq) << 4) + 4u * m;   // k = 16dq + 8 + 2m (+1)
 #pragma unroll
-          for (int t = 0; t < 32; ++t) {
-            const int tok = tok_base + col0 + t;
-            if (col0 + t < toks) {
-              const float f = __uint_as_float(v[t]);
-              if (slab != nullptr) slab[(size_t)tok * p.N + ch] = f;
-              else cptr[(size_t)tok * p.N + ch] = from_f32<T>(f);
-            }
+      for (int nb = 0; nb < 2; ++nb) {
+        if (nb < nblk && !(p.debug & 1)) {
+          const uint32_t wq[4] = {q[nb].x, q[nb].y, q[nb].z, q[nb].w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t w = wq[j];
+            const int row0 = nb * 64 + 16 * j + cq;
+            const uint32_t r0 = wt + row0 * 128;
+            const uint32_t r1 = r0 + 8 * 128;
+            const uint32_t x00 = lop3_and_or(w, 0x000f000fu, DQ<T>::MAGIC);
+            const uint32_t x01 = lop3_and_or(w >> 4, 0x000f000fu, DQ<T>::MAGIC);
+            const uint32_t x10 = lop3_and_or(w >> 8, 0x000f000fu, DQ<T>::MAGIC);
+            const uint32_t x11 = lop3_and_or(w >> 12, 0x000f000fu, DQ<T>::MAGIC);
+            sts32(r0 + a0, DQ<T>::sub_mul(x00, off2[nb][2 * j], s2[nb][2 * j]));
+            sts32(r0 + a1, DQ<T>::sub_mul(x01, off2[nb][2 * j], s2[nb][2 * j]));
+            sts32(r1 + a0, DQ<T>::sub_mul(x10, off2[nb][2 * j + 1], s2[nb][2 * j + 1]));
+            sts32(r1 + a1, DQ<T>::sub_mul(x11, off2[nb][2 * j + 1], s2[nb][2 * j + 1]));
           }
         }
       }
-      if (slab != nullptr) {
-        // split-k: every split stores its fp32 partial in its own slab; the LAST split to arrive on this
-        // tile's lock sums the slabs in a fixed order (deterministic, no atomics on data, no memset) and
-        // writes C, then returns the lock to zero — the reference's workspace contract.
-        __threadfence();
-        asm volatile("bar.sync 1, %0;" ::"n"(4 * MG_TEAMS * 32) : "memory");
-        const int tile = blockIdx.y * gridDim.x + blockIdx.x;
-        if (threadIdx.x == 96) *tmem_slot = (atomicAdd(p.locks + tile, 1) == p.split_k - 1) ? 1u : 0u;
-        asm volatile("bar.sync 1, %0;" ::"n"(4 * MG_TEAMS * 32) : "memory");
-        if (*tmem_slot != 0u) {
-          __threadfence();
-          if (ch_ok) {
-            for (int t = team; t < toks; t += MG_TEAMS) {
-              const size_t off = (size_t)(tok_base + t) * p.N + ch;
-              float acc = 0.f;
-              for (int z = 0; z < p.split_k; ++z) acc += __ldcg(p.c_tmp + (size_t)z * p.M * p.N + off);
-              cptr[off] = from_f32<T>(acc);
-            }
-          }
-          if (threadIdx.x == 96) p.locks[tile] = 0;
-        }
-      }
-      tc_fence_before();
+      if (!(p.debug & 8)) fence_proxy_async();   // generic-proxy stores -> visible to the tensor core's async proxy
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full_w[s]);
+      prefetch(c + MG_RING_DEPTH * MG_TEAMS);     // refill the slot just consumed (its words are in registers)
     }
+    cp_async_wait<0>();
+    if (prof && warp == 0 && lane == 0) { g_mg_prof[12] = (unsigned long long)(clock64() - t_role0); g_mg_prof[13] = w0; g_mg_prof[14] = w1; }
+
+    // ===================== epilogue: TMEM -> C =====================
+    mbar_wait(accum_full, 0);
+    tc_fence_after();
+    const int quad = warp & 3;                            // TMEM lanes 32*quad .. +31 belong to this warp
+    const int ch = n_base + quad * 32 + lane;
+    const bool ch_ok = ch < p.N;
+    T* cptr = reinterpret_cast<T*>(p.c);
+    float* slab = p.split_k > 1 ? p.c_tmp + (size_t)blockIdx.z * p.M * p.N : nullptr;
+    // the MG_TEAMS warps that share a lane quadrant interleave 32-column slabs
+    for (int col0 = team * 32; col0 < n_mma; col0 += 32 * MG_TEAMS) {
+      uint32_t v[32];
+      tmem_ld32(tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)col0, v);
+      if (ch_ok) {
+#pragma unroll
+        for (int t = 0; t < 32; ++t) {
+          const int tok = tok_base + col0 + t;
+          if (col0 + t < toks) {
+            const float f = __uint_as_float(v[t]);
+            if (slab != nullptr) slab[(size_t)tok * p.N + ch] = f;
+            else cptr[(size_t)tok * p.N + ch] = from_f32<T>(f);
+          }
+        }
+      }
+    }
+    if (slab != nullptr) {
+      // split-k: every split stores its fp32 partial in its own slab, then all splits of the tile meet on the
+      // tile's lock (the grid fits the GPU when the plan splits k, so every CTA is resident) and EACH reduces
+      // an interleaved 1/split_k share of the token rows over the slabs in a fixed order: deterministic, no
+      // atomics on data, no memset, no second kernel. The last CTA through returns the lock to zero — the
+      // reference's workspace contract (kernels/torch_bindings.cpp:167-176).
+      constexpr int EPI = MG_DQ_WARPS * 32;
+      const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+      int* lock = p.locks + tile;
+      __threadfence();
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI) : "memory");
+      if (threadIdx.x == 0) {
+        atomicAdd(lock, 1);
+        while (atomicAdd(lock, 0) < p.split_k) __nanosleep(64);
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI) : "memory");
+      __threadfence();
+      const int nvalid = min(MG_NT, p.N - n_base);               // channels of this tile (64 or 128)
+      if (lane * 4 < nvalid) {
+        for (int r = blockIdx.z + p.split_k * warp; r < toks; r += p.split_k * MG_DQ_WARPS) {
+          const size_t off = (size_t)(tok_base + r) * p.N + n_base + lane * 4;
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int z = 0; z < p.split_k; ++z) {
+            const float4 v = __ldcg(reinterpret_cast<const float4*>(p.c_tmp + (size_t)z * p.M * p.N + off));
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+          }
+          uint2 o;
+          o.x = pack2<T>(acc.x, acc.y);
+          o.y = pack2<T>(acc.z, acc.w);
+          *reinterpret_cast<uint2*>(cptr + off) = o;
+        }
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI) : "memory");
+      if (threadIdx.x == 0) {
+        if (atomicAdd(lock, 1) == 2 * p.split_k - 1) atomicExch(lock, 0);
+      }
+    }
+    if (prof && warp == 0 && lane == 0) g_mg_prof[15] = (unsigned long long)(clock64() - t_role0);
+    tc_fence_before();
   }
   __syncthreads();
-  if (warp == 0) {
+  if (warp == MG_WARP_TMA) {
     tc_fence_after();
     tmem_dealloc(tmem_d, tmem_cols);
   }
@@ -477,17 +521,24 @@ static int launch_marlin(const CUtensorMap& tmap, const MarlinParams& p, cudaStr
   int dev = 0;
   B200_CUDA_OK(cudaGetDevice(&dev));
   if (!(attr_done >> (dev & 63) & 1)) {
-    B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_SMEM));
+    B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_SMEM_TOTAL));
     attr_done |= 1ull << (dev & 63);
   }
   dim3 grid((p.N + MG_NT - 1) / MG_NT, (p.M + MG_TOK - 1) / MG_TOK, p.split_k);
-  kern<<<grid, MG_THREADS, MG_SMEM, st>>>(tmap, p);
+  const size_t smem = (size_t)p.stages * (p.act_bytes + MG_W_BYTES) + MG_SMEM_FIXED;
+  kern<<<grid, MG_THREADS, smem, st>>>(tmap, p);
   return check_launch("marlin_w4a16_tc5_kernel");
 }
 
 }  // namespace b200
 
 using namespace b200;
+
+extern "C" int b200_debug_marlin_prof(unsigned long long* out32) {
+  B200_CUDA_OK(cudaDeviceSynchronize());
+  B200_CUDA_OK(cudaMemcpyFromSymbol(out32, g_mg_prof, sizeof(unsigned long long) * 32));
+  return 0;
+}
 
 extern "C" int b200_marlin_gemm_plan(int size_m, int size_n, int size_k, int num_groups) {
   const int gs = num_groups > 1 ? size_k / num_groups : -1;
@@ -515,6 +566,8 @@ extern "C" int b200_gptq_marlin_gemm(const void* a, const void* b_q_weight, cons
   B200_CHECK(split_k == 1 || (c_tmp != nullptr && workspace != nullptr),
              "split-k needs the fp32 partial buffer [split_k, M, N] and the zeroed lock workspace");
   {
+    const int tiles = ((size_n + MG_NT - 1) / MG_NT) * ((size_m + MG_TOK - 1) / MG_TOK);
+    while (split_k > 1 && tiles * split_k > num_sms()) --split_k;   // all splits of a tile must be co-resident
     const int chunks_total = size_k / MG_KC;
     while (split_k > 1 && (split_k - 1) * ((chunks_total + split_k - 1) / split_k) >= chunks_total) --split_k;
   }
@@ -533,12 +586,19 @@ extern "C" int b200_gptq_marlin_gemm(const void* a, const void* b_q_weight, cons
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   B200_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed: " + std::to_string((int)r));
-
   MarlinParams p{};
   p.b_q = (const uint32_t*)b_q_weight; p.scales = b_scales; p.zeros = (const uint32_t*)b_zeros;
   p.c = c; p.c_tmp = c_tmp; p.locks = workspace; p.M = size_m; p.N = size_n; p.K = size_k; p.group_size = gs;
   p.split_k = split_k;
   p.box_rows = box_rows;
+  {
+    const char* dbg = getenv("B200_MARLIN_DEBUG");
+    p.debug = dbg ? atoi(dbg) : 0;
+  }
+  p.act_bytes = (box_rows * 128 + 1023) & ~1023;
+  // shared-memory plan: as many MMA stages (activation tile + dequantised weight tile) as fit, 2..8
+  p.stages = (MG_SMEM_TOTAL - MG_SMEM_FIXED) / (p.act_bytes + MG_W_BYTES);
+  if (p.stages > MG_MAX_STAGES) p.stages = MG_MAX_STAGES;
   p.grouped = (gs > 0 && gs < size_k) ? 1 : 0;
   p.rows_per_chunk = (gs > 0 && gs < MG_KC) ? MG_KC / gs : 1;
   p.chunks_per_group = (gs > MG_KC) ? gs / MG_KC : 1;

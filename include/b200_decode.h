@@ -162,6 +162,8 @@ int b200_activation(void* out, const void* input, int num_tokens, int d, int act
  * torch_bindings.cpp:167-176). The last split to arrive sums the partial slabs in a fixed order
  * (deterministic). split_k <= 0 = use the plan. 4-bit only (uint4b8, uint4+zp); act-order (g_idx/perm) is not supported. */
 int b200_marlin_gemm_plan(int size_m, int size_n, int size_k, int num_groups);
+/* debug only: per-role cycle attribution of the last GEMM launched with B200_MARLIN_DEBUG & 16 (32 x u64) */
+int b200_debug_marlin_prof(unsigned long long* out32);
 int b200_gptq_marlin_gemm(const void* a, const void* b_q_weight, const void* b_scales,
                           const void* b_zeros, void* c, float* c_tmp, int32_t* workspace,
                           int size_m, int size_n, int size_k, int num_groups, int num_bits,
