@@ -53,10 +53,20 @@ SIGNATURES = {
     "b200_awq_marlin_repack": [c_void_p] * 2 + [c_int] * 3 + [c_void_p],
     "b200_moe_align_block_size": [c_void_p, c_int, c_int64, c_int, c_int] + [c_void_p] * 4,
     "b200_topk_softmax": [c_void_p] * 4 + [c_int] * 3 + [c_void_p],
+    "b200_car_meta_size": [],
+    "b200_car_init": [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_int],
+    "b200_car_dispose": [c_int64],
+    "b200_car_register_buffer": [c_int64, c_void_p, c_void_p, c_void_p],
+    "b200_car_all_reduce": [c_int64, c_void_p, c_void_p, c_int64, c_int, c_void_p],
+    "b200_car_get_graph_buffer_ipc_meta": [c_int64, c_void_p, c_void_p, c_int],
+    "b200_car_register_graph_buffers": [c_int64, c_void_p, c_void_p, c_int],
     "b200_get_device_attribute": [c_int64, c_int64],
     "b200_get_max_shared_memory_per_block_device_attribute": [c_int64],
 }
 _RESTYPES = {
+    "b200_car_meta_size": c_int64,
+    "b200_car_init": c_int64,
+    "b200_car_dispose": None,
     "b200_last_error": ctypes.c_char_p,
     "b200_get_device_attribute": c_int64,
     "b200_get_max_shared_memory_per_block_device_attribute": c_int64,

@@ -16,7 +16,9 @@
 #include <torch/custom_class.h>
 #include <ATen/core/stack.h>
 
+#include <stdexcept>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "b200_decode.h"
@@ -417,6 +419,96 @@ torch::Tensor awq_marlin_repack_meta(torch::Tensor& b_q_weight, c10::SymInt size
   return torch::empty_symint({size_k / 16, size_n * 16 / pf}, b_q_weight.options());
 }
 
+// ---- custom all-reduce (kernels/all_reduce/custom_all_reduce.cu:15-141) ---------------------------------------
+using fptr_t = int64_t;
+
+std::string pack_handles(const std::vector<std::string>& handles) {
+  std::string blob;
+  for (const auto& h : handles) {
+    TORCH_CHECK(h.size() == 64, "IPC handle must be 64 bytes, got ", h.size());
+    blob += h;
+  }
+  return blob;
+}
+
+fptr_t init_custom_ar(torch::Tensor& meta, torch::Tensor& rank_data, const std::vector<std::string>& handles,
+                      const std::vector<int64_t>& offsets, int64_t rank, bool full_nvlink) {
+  const int world_size = (int)offsets.size();
+  if (world_size > 8) throw std::invalid_argument("world size > 8 is not supported");
+  if (world_size % 2 != 0) throw std::invalid_argument("Odd num gpus is not supported for now");
+  if (world_size != (int)handles.size()) throw std::invalid_argument("handles length should equal to offsets length");
+  if (rank < 0 || rank >= world_size) throw std::invalid_argument("invalid rank passed in");
+  const at::cuda::OptionalCUDAGuard guard(device_of(meta));
+  const std::string blob = pack_handles(handles);
+  const fptr_t fa = b200_car_init(meta.data_ptr(), rank_data.data_ptr(), rank_data.numel() * rank_data.element_size(),
+                                  blob.data(), offsets.data(), world_size, (int)rank, full_nvlink ? 1 : 0);
+  TORCH_CHECK(fa != 0, b200_last_error());
+  return fa;
+}
+
+bool is_weak_contiguous(const torch::Tensor& t) {
+  return t.is_contiguous() || (t.storage().nbytes() - t.storage_offset() * t.element_size() ==
+                               (size_t)(t.numel() * t.element_size()));
+}
+
+void all_reduce_reg(fptr_t fa, torch::Tensor& inp, torch::Tensor& out) {
+  const at::cuda::OptionalCUDAGuard guard(device_of(inp));
+  TORCH_CHECK_EQ(inp.scalar_type(), out.scalar_type());
+  TORCH_CHECK_EQ(inp.numel(), out.numel());
+  TORCH_CHECK(is_weak_contiguous(out));
+  check(b200_car_all_reduce(fa, inp.data_ptr(), out.data_ptr(), out.numel(), dtype_code(out, "custom allreduce"),
+                            cur_stream()));
+}
+
+void all_reduce_unreg(fptr_t fa, torch::Tensor& inp, torch::Tensor& reg_buffer, torch::Tensor& out) {
+  const at::cuda::OptionalCUDAGuard guard(device_of(inp));
+  const size_t input_size = inp.numel() * inp.element_size();
+  TORCH_CHECK_EQ(inp.scalar_type(), out.scalar_type());
+  TORCH_CHECK_EQ(inp.numel(), out.numel());
+  TORCH_CHECK(input_size <= (size_t)(reg_buffer.numel() * reg_buffer.element_size()),
+              "registered buffer is too small to contain the input");
+  TORCH_CHECK(is_weak_contiguous(out));
+  AT_CUDA_CHECK(cudaMemcpyAsync(reg_buffer.data_ptr(), inp.data_ptr(), input_size, cudaMemcpyDeviceToDevice,
+                                (cudaStream_t)cur_stream()));
+  check(b200_car_all_reduce(fa, reg_buffer.data_ptr(), out.data_ptr(), out.numel(),
+                            dtype_code(out, "custom allreduce"), cur_stream()));
+}
+
+void dispose(fptr_t fa) { b200_car_dispose(fa); }
+int64_t meta_size() { return b200_car_meta_size(); }
+
+void register_buffer(fptr_t fa, torch::Tensor& t, const std::vector<std::string>& handles,
+                     const std::vector<int64_t>& offsets) {
+  const at::cuda::OptionalCUDAGuard guard(device_of(t));
+  const std::string blob = pack_handles(handles);
+  check(b200_car_register_buffer(fa, t.data_ptr(), blob.data(), offsets.data()));
+}
+
+std::tuple<torch::Tensor, std::vector<int64_t>> get_graph_buffer_ipc_meta(fptr_t fa) {
+  const int n = b200_car_get_graph_buffer_ipc_meta(fa, nullptr, nullptr, 0);
+  TORCH_CHECK(n >= 0, b200_last_error());
+  auto handles = torch::empty({(int64_t)n * 64}, torch::TensorOptions().dtype(torch::kUInt8).device(torch::kCPU));
+  std::vector<int64_t> offsets(n);
+  if (n > 0)
+    TORCH_CHECK(b200_car_get_graph_buffer_ipc_meta(fa, handles.data_ptr(), offsets.data(), n) == n, b200_last_error());
+  return {handles, std::move(offsets)};
+}
+
+void register_graph_buffers(fptr_t fa, const std::vector<std::string>& handles,
+                            const std::vector<std::vector<int64_t>>& offsets) {
+  const size_t ws = handles.size();
+  TORCH_CHECK(ws == offsets.size() && ws > 0, "handles / offsets length mismatch");
+  const size_t n = offsets[0].size();
+  std::string blob;
+  std::vector<int64_t> flat;
+  for (size_t r = 0; r < ws; ++r) {
+    TORCH_CHECK(handles[r].size() == n * 64 && offsets[r].size() == n, "per-rank graph buffer meta size mismatch");
+    blob += handles[r];
+    flat.insert(flat.end(), offsets[r].begin(), offsets[r].end());
+  }
+  check(b200_car_register_graph_buffers(fa, blob.data(), flat.data(), (int)n));
+}
+
 }  // namespace
 
 TORCH_LIBRARY(_C, ops) {
@@ -540,6 +632,26 @@ TORCH_LIBRARY(_C_cuda_utils, cuda_utils) {
   cuda_utils.def("get_max_shared_memory_per_block_device_attribute(int device_id) -> int");
   cuda_utils.impl("get_max_shared_memory_per_block_device_attribute",
                   &get_max_shared_memory_per_block_device_attribute);
+}
+
+TORCH_LIBRARY(_C_custom_ar, custom_ar) {
+  custom_ar.def(
+      "init_custom_ar(Tensor meta, Tensor rank_data, "
+      "str[] handles, int[] offsets, int rank, "
+      "bool full_nvlink) -> int");
+  custom_ar.impl("init_custom_ar", torch::kCUDA, &init_custom_ar);
+  custom_ar.def("all_reduce_reg(int fa, Tensor inp, Tensor! out) -> ()");
+  custom_ar.impl("all_reduce_reg", torch::kCUDA, &all_reduce_reg);
+  custom_ar.def("all_reduce_unreg(int fa, Tensor inp, Tensor reg_buffer, Tensor! out) -> ()");
+  custom_ar.impl("all_reduce_unreg", torch::kCUDA, &all_reduce_unreg);
+  custom_ar.def("dispose", &dispose);
+  custom_ar.def("meta_size", &meta_size);
+  custom_ar.def(
+      "register_buffer(int fa, Tensor t, str[] handles, "
+      "int[] offsets) -> ()");
+  custom_ar.impl("register_buffer", torch::kCUDA, &register_buffer);
+  custom_ar.def("get_graph_buffer_ipc_meta", &get_graph_buffer_ipc_meta);
+  custom_ar.def("register_graph_buffers", &register_graph_buffers);
 }
 
 // `import <pkg>._C` support (kernels/core/registration.h:22-27 of the reference does the same)

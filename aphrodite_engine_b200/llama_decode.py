@@ -62,7 +62,7 @@ class LlamaDecoder:
     def __init__(self, shape: LlamaShape, batch: int, block_size: int, num_blocks: int,
                  device, dtype=torch.bfloat16, kv_cache_dtype: str = "auto", tp_rank: int = 0,
                  tp_size: int = 1, group=None, seed: int = 1234, layers: Optional[int] = None,
-                 kv_fill: bool = True):
+                 kv_fill: bool = True, quant: Optional[str] = None, group_size: int = 128):
         assert shape.heads % tp_size == 0 and shape.kv_heads % tp_size == 0
         assert shape.intermediate % tp_size == 0 and shape.vocab % tp_size == 0
         self.s, self.batch, self.block_size = shape, batch, block_size
@@ -81,6 +81,26 @@ class LlamaDecoder:
         def w(*sz, std=0.02):
             return (torch.randn(*sz, generator=g, device=device, dtype=torch.float32) * std).to(dtype)
 
+        self.quant = quant
+        if quant == "gptq":
+            # GPTQ 4-bit (uint4b8, group 128) in Marlin layout — BASELINE configs[2]. Random packed words and
+            # scales stand in for a checkpoint (the `dummy` load format); the layouts are what
+            # gptq_marlin_repack / marlin_permute_scales would produce (process_weights_after_loading,
+            # aphrodite/quantization/kernels/marlin.py:89-109).
+            from .scalar_type import scalar_types
+            self._qtype = scalar_types.uint4b8
+            self._empty = torch.empty(0, dtype=torch.int32, device=device)
+
+            def qw(n_out, k_in):
+                return dict(q=torch.randint(-2**31, 2**31 - 1, (k_in // 16, n_out * 2), generator=g,
+                                            device=device, dtype=torch.int32),
+                            s=(torch.rand(k_in // group_size, n_out, generator=g, device=device) * 0.004 + 0.001).to(dtype),
+                            ws=torch.zeros((n_out // 64) * 16, dtype=torch.int32, device=device), n=n_out, k=k_in)
+            w_lin = qw
+        else:
+            def w_lin(n_out, k_in):
+                return w(n_out, k_in)
+
         H = shape.hidden
         self.embed = w(shape.vocab, H)
         self.layers = []
@@ -88,10 +108,10 @@ class LlamaDecoder:
             self.layers.append(dict(
                 ln1=torch.ones(H, dtype=dtype, device=device),
                 ln2=torch.ones(H, dtype=dtype, device=device),
-                qkv=w(self.q_size + 2 * self.kv_size, H),
-                o=w(H, self.q_size),
-                gate_up=w(2 * self.inter, H),
-                down=w(H, self.inter),
+                qkv=w_lin(self.q_size + 2 * self.kv_size, H),
+                o=w_lin(H, self.q_size),
+                gate_up=w_lin(2 * self.inter, H),
+                down=w_lin(H, self.inter),
             ))
         self.norm = torch.ones(H, dtype=dtype, device=device)
         self.lm_head = w(self.vocab_local, H)
@@ -117,7 +137,15 @@ class LlamaDecoder:
         self.kv_views = [PagedAttention.split_kv_cache(kv, self.kv_heads, shape.head_size)
                          for kv in self.kv_caches]
         self.attn_hook: Optional[Callable] = None   # bench instrumentation around the attention op
-        self.my_kernel_launches_per_step = 6 * self.n_layers + 1
+        self.my_kernel_launches_per_step = (10 if quant == "gptq" else 6) * self.n_layers + 1
+
+    def _linear(self, x, wt):
+        """F.linear for bf16 weights (cuBLAS, as the reference's UnquantizedLinearMethod) or the Marlin-format
+        W4A16 GEMM (apply_gptq_marlin_linear, aphrodite/quantization/utils/marlin_utils.py:241-275)."""
+        if isinstance(wt, dict):
+            return ops.gptq_marlin_gemm(x, wt["q"], wt["s"], self._empty, self._empty, self._empty, wt["ws"],
+                                        self._qtype, x.shape[0], wt["n"], wt["k"], True, False, True, False)
+        return F.linear(x, wt)
 
     def _all_reduce(self, x):
         if self.tp_size > 1:
@@ -136,7 +164,7 @@ class LlamaDecoder:
                 hidden = normed
             else:
                 ops.fused_add_rms_norm(hidden, residual, L["ln1"], s.rms_eps)
-            qkv = F.linear(hidden, L["qkv"])
+            qkv = self._linear(hidden, L["qkv"])
             q, k, v = qkv.split([self.q_size, self.kv_size, self.kv_size], dim=-1)
             ops.rotary_embedding(st.positions, q, k, s.head_size, self.cos_sin, True)
             kc, vc = self.kv_views[li]
@@ -153,12 +181,12 @@ class LlamaDecoder:
                                           1.0, output=attn_out)
             if self.attn_hook is not None:
                 self.attn_hook(li, False)
-            hidden = self._all_reduce(F.linear(attn_out.view(self.batch, -1), L["o"]))
+            hidden = self._all_reduce(self._linear(attn_out.view(self.batch, -1), L["o"]))
             ops.fused_add_rms_norm(hidden, residual, L["ln2"], s.rms_eps)
-            gate_up = F.linear(hidden, L["gate_up"])
+            gate_up = self._linear(hidden, L["gate_up"])
             act = torch.empty(self.batch, self.inter, dtype=self.dtype, device=self.device)
             ops.silu_and_mul(act, gate_up)
-            hidden = self._all_reduce(F.linear(act, L["down"]))
+            hidden = self._all_reduce(self._linear(act, L["down"]))
         ops.fused_add_rms_norm(hidden, residual, self.norm, s.rms_eps)
         logits = F.linear(hidden, self.lm_head)
         if self.tp_size == 1:

@@ -53,6 +53,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-layers", type=int, default=2)
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--quant", default=None, choices=[None, "gptq"],
+                    help="gptq = BASELINE configs[2] (GPTQ int4 Marlin W4A16 linears); default bf16 = configs[1]")
     return ap.parse_args()
 
 
@@ -265,7 +267,7 @@ def run_b200(args):
     shape = LlamaShape(layers=args.layers)
     host, num_blocks = make_synthetic_batch(args.batch, args.ctx, args.block_size)
     model = LlamaDecoder(shape, args.batch, args.block_size, num_blocks, dev, torch.bfloat16,
-                         args.kv_cache_dtype, tp_rank=rank, tp_size=world, group=group)
+                         args.kv_cache_dtype, tp_rank=rank, tp_size=world, group=group, quant=args.quant)
     st = DecodeState(args.batch, host["block_tables"].shape[1], dev)
     h2d_bytes = upload(st, host)
     torch.cuda.synchronize()
@@ -388,7 +390,8 @@ def run_b200(args):
         "steps": K, "warmup": W, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"Llama-3-8B bf16 paged-attention decode bs={args.batch} ctx={args.ctx} "
-                               f"block={args.block_size} layers={shape.layers} (BASELINE configs[1])",
+                               f"block={args.block_size} layers={shape.layers} "
+                               + ("GPTQ int4 Marlin W4A16 linears (BASELINE configs[2])" if args.quant else "(BASELINE configs[1])"),
                    "parallelism": f"tp{world}", "kv_cache_dtype": args.kv_cache_dtype,
                    "cuda_graph": graph is not None, "l2": "working set (KV + weights) >> 126 MB L2, no flush needed"},
         "e2e": {"value": args.batch / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,

@@ -188,6 +188,27 @@ int b200_moe_align_block_size(const void* topk_ids, int ids_are_int64, int64_t n
 int b200_topk_softmax(float* topk_weights, int32_t* topk_indices, int32_t* token_expert_indices,
                       const float* gating_output, int num_tokens, int num_experts, int topk, void* stream);
 
+/* ---- custom all-reduce over NVLink peer memory ---------------------------------------------------
+ * replaces init_custom_ar / all_reduce_reg / all_reduce_unreg / dispose / meta_size / register_buffer /
+ *          get_graph_buffer_ipc_meta / register_graph_buffers
+ *          kernels/all_reduce/custom_all_reduce.cu:15-141 (schemas kernels/torch_bindings.cpp:510-535)
+ * `meta`: this rank's device allocation [b200_car_meta_size() bytes of signals | scratch >= max message bytes],
+ * zero-initialised; `rank_data`: device scratch for peer-pointer tables; `handles`: world_size x 64-byte
+ * cudaIpcMemHandle_t (rank order; the own entry is ignored), `offsets`: byte offset of each rank's buffer inside
+ * its IPC allocation. Returns an opaque handle (0 on error). world_size in {2,4,6,8}. */
+int64_t b200_car_meta_size(void);
+int64_t b200_car_init(void* meta, void* rank_data, int64_t rank_data_bytes, const void* handles,
+                      const int64_t* offsets, int world_size, int rank, int full_nvlink);
+void b200_car_dispose(int64_t fa);
+int b200_car_register_buffer(int64_t fa, void* self_ptr, const void* handles, const int64_t* offsets);
+/* inp must be a registered buffer, or the call must happen under stream capture (its address is then recorded
+ * and registered afterwards with the two calls below). out may be any device buffer. */
+int b200_car_all_reduce(int64_t fa, const void* inp, void* out, int64_t numel, int dtype, void* stream);
+/* handles_out == NULL: returns the number of recorded graph buffers; otherwise fills n x 64-byte handles + offsets */
+int b200_car_get_graph_buffer_ipc_meta(int64_t fa, void* handles_out, int64_t* offsets_out, int capacity);
+/* handles: [world_size][n] x 64 bytes, offsets: [world_size][n] */
+int b200_car_register_graph_buffers(int64_t fa, const void* handles, const int64_t* offsets, int n);
+
 /* ---- device queries -----------------------------------------------------------------------------
  * replaces get_device_attribute / get_max_shared_memory_per_block_device_attribute
  *          kernels/cuda_utils_kernels.cu (schema torch_bindings.cpp:497-504) */

@@ -1,0 +1,97 @@
+"""Multi-GPU parity (>= 2 GPUs on the box): the NVLink peer-memory all-reduce vs NCCL, eager and under CUDA graph
+capture, small integers so sums are exact — the reference's tests/distributed/test_custom_all_reduce.py:55-81."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    try:
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        torch.cuda.set_device(rank)
+        dev = torch.device("cuda", rank)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+        cpu_group = dist.new_group(backend="gloo")
+        from aphrodite_engine_b200.distributed import CustomAllreduce
+        ca = CustomAllreduce(cpu_group, dev)
+        assert not ca.disabled, "P2P access between the GPUs of this box is required"
+        ok = True
+        msgs = []
+        for dtype in (torch.float32, torch.float16, torch.bfloat16):
+            for numel in (8, 1024, 4096 + 8, 256 * 4096, 1024 * 4096, 2097152 + 64):
+                if numel * torch.tensor([], dtype=dtype).element_size() > ca.max_size:
+                    continue
+                torch.manual_seed(numel + rank)
+                x = torch.randint(1, 16, (numel,), dtype=dtype, device=dev)
+                ref = x.clone()
+                dist.all_reduce(ref)
+                out = ca.custom_all_reduce(x)                  # eager: staged through the registered buffer
+                torch.cuda.synchronize()
+                if out is None or not torch.equal(out, ref):
+                    ok = False
+                    msgs.append(f"eager {dtype} {numel}")
+        # CUDA graph: addresses recorded during capture, registered afterwards
+        inp1 = torch.randint(1, 16, (256, 4096), dtype=torch.bfloat16, device=dev)
+        inp2 = torch.randint(1, 16, (1024,), dtype=torch.float32, device=dev)
+        dist.barrier()
+        torch.cuda.synchronize()
+        with ca.capture():
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                o1 = ca.custom_all_reduce(inp1)
+                o2 = ca.custom_all_reduce(inp2)
+                o3 = ca.custom_all_reduce(o1)                  # chained: an intermediate graph buffer as input
+        for it in range(3):
+            inp1.copy_(torch.randint(1, 8, inp1.shape, device=dev).to(inp1.dtype))
+            inp2.copy_(torch.randint(1, 8, inp2.shape, device=dev).to(inp2.dtype))
+            graph.replay()
+            torch.cuda.synchronize()
+            r1, r2 = inp1.clone(), inp2.clone()
+            dist.all_reduce(r1)
+            dist.all_reduce(r2)
+            r3 = r1.clone()
+            dist.all_reduce(r3)
+            if not (torch.equal(o1, r1) and torch.equal(o2, r2) and torch.equal(o3, r3)):
+                ok = False
+                msgs.append(f"graph replay {it}")
+        q.put((rank, ok, msgs))
+        dist.barrier()
+        torch.cuda.synchronize()
+        ca.close()
+    except Exception as e:  # report instead of hanging the parent
+        import traceback
+        q.put((rank, False, [repr(e), traceback.format_exc()]))
+    finally:
+        os._exit(0)
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_custom_all_reduce_matches_nccl(world):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=30)
+    for rank, ok, msgs in res:
+        assert ok, f"rank {rank}: {msgs}"
