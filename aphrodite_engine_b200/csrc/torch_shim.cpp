@@ -425,8 +425,15 @@ using fptr_t = int64_t;
 std::string pack_handles(const std::vector<std::string>& handles) {
   std::string blob;
   for (const auto& h : handles) {
-    TORCH_CHECK(h.size() == 64, "IPC handle must be 64 bytes, got ", h.size());
-    blob += h;
+    // torch <= 2.4 (the reference's pin) shares the raw 64-byte cudaIpcMemHandle_t; newer caching allocators
+    // prefix it with {version, type}: type 'c' = cudaMalloc block (usable), 'e' = expandable segment (not IPC-able)
+    if (h.size() == 66) {
+      TORCH_CHECK(h[1] == 'c', "custom allreduce needs cudaMalloc-backed buffers (expandable_segments is not supported)");
+      blob += h.substr(2);
+    } else {
+      TORCH_CHECK(h.size() == 64, "IPC handle must be 64 bytes, got ", h.size());
+      blob += h;
+    }
   }
   return blob;
 }

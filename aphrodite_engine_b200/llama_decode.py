@@ -62,12 +62,14 @@ class LlamaDecoder:
     def __init__(self, shape: LlamaShape, batch: int, block_size: int, num_blocks: int,
                  device, dtype=torch.bfloat16, kv_cache_dtype: str = "auto", tp_rank: int = 0,
                  tp_size: int = 1, group=None, seed: int = 1234, layers: Optional[int] = None,
-                 kv_fill: bool = True, quant: Optional[str] = None, group_size: int = 128):
+                 kv_fill: bool = True, quant: Optional[str] = None, group_size: int = 128,
+                 custom_ar=None):
         assert shape.heads % tp_size == 0 and shape.kv_heads % tp_size == 0
         assert shape.intermediate % tp_size == 0 and shape.vocab % tp_size == 0
         self.s, self.batch, self.block_size = shape, batch, block_size
         self.device, self.dtype, self.kv_cache_dtype = device, dtype, kv_cache_dtype
         self.tp_rank, self.tp_size, self.group = tp_rank, tp_size, group
+        self.custom_ar = custom_ar      # distributed.CustomAllreduce or None (-> NCCL)
         self.n_layers = shape.layers if layers is None else layers
         self.heads = shape.heads // tp_size
         self.kv_heads = shape.kv_heads // tp_size
@@ -148,7 +150,13 @@ class LlamaDecoder:
         return F.linear(x, wt)
 
     def _all_reduce(self, x):
+        """Row-parallel reduction (GroupCoordinator._all_reduce, aphrodite/distributed/parallel_state.py:353-379):
+        the NVLink peer-memory kernel when it applies (out of place), else NCCL in place."""
         if self.tp_size > 1:
+            if self.custom_ar is not None:
+                out = self.custom_ar.custom_all_reduce(x)
+                if out is not None:
+                    return out
             torch.distributed.all_reduce(x, group=self.group)
         return x
 

@@ -53,6 +53,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-layers", type=int, default=2)
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--allreduce", default="custom", choices=["custom", "nccl"],
+                    help="TP all-reduce: NVLink peer-memory kernel (default) or NCCL")
     ap.add_argument("--quant", default=None, choices=[None, "gptq"],
                     help="gptq = BASELINE configs[2] (GPTQ int4 Marlin W4A16 linears); default bf16 = configs[1]")
     return ap.parse_args()
@@ -259,15 +261,20 @@ def run_b200(args):
     assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node == --gpus"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    group = None
+    group, ca = None, None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
         group = dist.group.WORLD
+        if args.allreduce == "custom":
+            from aphrodite_engine_b200.distributed import CustomAllreduce
+            ca = CustomAllreduce(dist.new_group(backend="gloo"), dev)
+            if ca.disabled:
+                ca = None
 
     shape = LlamaShape(layers=args.layers)
     host, num_blocks = make_synthetic_batch(args.batch, args.ctx, args.block_size)
     model = LlamaDecoder(shape, args.batch, args.block_size, num_blocks, dev, torch.bfloat16,
-                         args.kv_cache_dtype, tp_rank=rank, tp_size=world, group=group, quant=args.quant)
+                         args.kv_cache_dtype, tp_rank=rank, tp_size=world, group=group, quant=args.quant, custom_ar=ca)
     st = DecodeState(args.batch, host["block_tables"].shape[1], dev)
     h2d_bytes = upload(st, host)
     torch.cuda.synchronize()
@@ -280,9 +287,11 @@ def run_b200(args):
         stream.synchronize()
         if not args.no_graph:
             try:
+                import contextlib
                 graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph, stream=stream):
-                    model.forward(st)
+                with (ca.capture() if ca is not None else contextlib.nullcontext()):
+                    with torch.cuda.graph(graph, stream=stream):
+                        model.forward(st)
             except Exception as e:       # keep measuring, eagerly, and say so
                 graph = None
                 if rank == 0:
@@ -392,7 +401,7 @@ def run_b200(args):
         "config": {"workload": f"Llama-3-8B bf16 paged-attention decode bs={args.batch} ctx={args.ctx} "
                                f"block={args.block_size} layers={shape.layers} "
                                + ("GPTQ int4 Marlin W4A16 linears (BASELINE configs[2])" if args.quant else "(BASELINE configs[1])"),
-                   "parallelism": f"tp{world}", "kv_cache_dtype": args.kv_cache_dtype,
+                   "parallelism": f"tp{world}", "allreduce": ("nvlink-p2p" if ca is not None else ("nccl" if world > 1 else "none")), "kv_cache_dtype": args.kv_cache_dtype,
                    "cuda_graph": graph is not None, "l2": "working set (KV + weights) >> 126 MB L2, no flush needed"},
         "e2e": {"value": args.batch / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e},
