@@ -252,6 +252,10 @@ def run_reference_arm(args, rank):
 # CUDA arm
 # ================================================================================================
 def run_b200(args):
+    # keep stdout to exactly ONE JSON line: libraries (NCCL prints its version banner) write to fd 1 too
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    os.environ.setdefault("NCCL_DEBUG", "WARN")
     import torch.distributed as dist
     from aphrodite_engine_b200.llama_decode import (DecodeState, LlamaDecoder, LlamaShape,
                                                     make_synthetic_batch, upload)
@@ -418,7 +422,7 @@ def run_b200(args):
         except Exception as e:  # never lose the GPU numbers to a host-side problem
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "error": repr(e)}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         # Tear-down: NCCL communicators captured in a live CUDA graph can block destroy_process_group();
         # everything has been measured and printed, so synchronise and leave without running destructors.
