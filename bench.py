@@ -53,8 +53,10 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-layers", type=int, default=2)
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--allreduce", default="custom", choices=["custom", "nccl"],
-                    help="TP all-reduce: NVLink peer-memory kernel (default) or NCCL")
+    ap.add_argument("--allreduce", default="auto", choices=["auto", "custom", "nccl"],
+                    help="TP all-reduce: NVLink peer-memory kernel or NCCL; auto = the peer-memory kernel up to 4 "
+                         "ranks (verified bit-exact vs NCCL on 2 and 4 GPUs), NCCL at 8 (same speed there, and the "
+                         "8-rank parity run of this round was inconclusive)")
     ap.add_argument("--quant", default=None, choices=[None, "gptq"],
                     help="gptq = BASELINE configs[2] (GPTQ int4 Marlin W4A16 linears); default bf16 = configs[1]")
     return ap.parse_args()
@@ -269,7 +271,7 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
         group = dist.group.WORLD
-        if args.allreduce == "custom":
+        if args.allreduce == "custom" or (args.allreduce == "auto" and world <= 4):
             from aphrodite_engine_b200.distributed import CustomAllreduce
             ca = CustomAllreduce(dist.new_group(backend="gloo"), dev)
             if ca.disabled:

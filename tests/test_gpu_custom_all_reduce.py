@@ -60,12 +60,13 @@ def _worker(rank, world, port, q):
             inp2.copy_(torch.randint(1, 8, inp2.shape, device=dev).to(inp2.dtype))
             graph.replay()
             torch.cuda.synchronize()
-            r1, r2 = inp1.clone(), inp2.clone()
+            # exact references in fp32 (NCCL's 16-bit ring adds round odd partial sums above 256 at 8 ranks;
+            # the kernel under test accumulates in fp32 and rounds once, so it must equal the exact integers)
+            r1, r2 = inp1.float(), inp2.clone()
             dist.all_reduce(r1)
             dist.all_reduce(r2)
-            r3 = r1.clone()
-            dist.all_reduce(r3)
-            if not (torch.equal(o1, r1) and torch.equal(o2, r2) and torch.equal(o3, r3)):
+            r3 = r1 * world
+            if not (torch.equal(o1.float(), r1) and torch.equal(o2, r2) and torch.equal(o3.float(), r3)):
                 ok = False
                 msgs.append(f"graph replay {it}")
         q.put((rank, ok, msgs))
