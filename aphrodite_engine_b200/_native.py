@@ -53,6 +53,9 @@ SIGNATURES = {
     "b200_awq_marlin_repack": [c_void_p] * 2 + [c_int] * 3 + [c_void_p],
     "b200_moe_align_block_size": [c_void_p, c_int, c_int64, c_int, c_int] + [c_void_p] * 4,
     "b200_topk_softmax": [c_void_p] * 4 + [c_int] * 3 + [c_void_p],
+    "b200_permute_cols": [c_void_p] * 3 + [c_int64, c_int, c_void_p],
+    "b200_awq_dequantize": [c_void_p] * 4 + [c_int64, c_int, c_int, c_void_p],
+    "b200_advance_step_flashattn": [c_int] * 3 + [c_void_p] * 6 + [c_int64, c_void_p],
     "b200_car_meta_size": [],
     "b200_car_init": [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_int],
     "b200_car_dispose": [c_int64],

@@ -63,6 +63,7 @@ struct MarlinParams {
   int grouped;           // 1: b_scales has one row per k-group (Marlin "grouped" permutation), 0: single row
   int rows_per_chunk;    // scale rows a 64-wide chunk spans (1, or 2 when group_size == 32)
   int chunks_per_group;  // 64-wide chunks per scale group (>= 1)
+  int cpg_shift;         // log2(chunks_per_group) when it is a power of two, else -1
   int stages;            // act/weight pipeline depth (2..8), chosen from the token count
   int act_bytes;         // bytes of one activation stage (box_rows * 128, rounded up to 1024)
   int debug;             // B200_MARLIN_DEBUG (timing experiments only): 1 skip dequant math, 2 skip MMAs, 4 skip act TMA
@@ -210,8 +211,10 @@ marlin_w4a16_tc5_kernel(const __grid_constant__ CUtensorMap tmap_a, const Marlin
   uint8_t* w_s = act_s + (size_t)NS * p.act_bytes;             // [NS][128 x 128 B]        (dequantised weights)
   uint8_t* ring_s = w_s + (size_t)NS * MG_W_BYTES;             // [DQ_WARPS][DEPTH][slot]  (per-warp cp.async rings)
   uint64_t* bars = reinterpret_cast<uint64_t*>(ring_s + (size_t)MG_DQ_WARPS * MG_RING_DEPTH * MG_SLOT_BYTES);
-  uint64_t* full_act = bars;                        // [NS]  TMA tx
-  uint64_t* full_w = full_act + MG_MAX_STAGES;      // [NS]  4 dequant warps of one team
+  // one "stage ready" barrier per stage: 1 arrival + tx bytes from the activation TMA and 4 arrivals from the
+  // team that dequantised the weight tile (a single wait in the MMA issuer's loop instead of two)
+  uint64_t* full_w = bars;                          // [NS]
+  uint64_t* full_act = full_w;                      //  (same barriers)
   // "stage free" barriers, TWO per stage used alternately (use u of a stage signals empty[(u&1)][s]): a waiter
   // is then never two phases ahead of the barrier it tests, whatever the team / stage counts (a parity test
   // two phases ahead passes vacuously — the bug class of the attention ring)
@@ -233,8 +236,7 @@ marlin_w4a16_tc5_kernel(const __grid_constant__ CUtensorMap tmap_a, const Marlin
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < MG_MAX_STAGES; ++i) {
-      mbar_init(&full_act[i], 1);
-      mbar_init(&full_w[i], 4);
+      mbar_init(&full_w[i], 5);
       mbar_init(&empty[i], 1);
       mbar_init(&empty[MG_MAX_STAGES + i], 1);
     }
@@ -247,7 +249,7 @@ marlin_w4a16_tc5_kernel(const __grid_constant__ CUtensorMap tmap_a, const Marlin
   tc_fence_after();
   const uint32_t tmem_d = *tmem_slot;
   const bool prof = (p.debug & 16) && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
-  unsigned long long w0 = 0, w1 = 0;
+  unsigned long long w0 = 0, w1 = 0, w2 = 0, w3 = 0;
   const long long t_role0 = clock64();
 
   // Warp roles. The two single-thread roles sit in the HIGHEST warp ids: the issue arbiter favours high warp
@@ -256,9 +258,11 @@ marlin_w4a16_tc5_kernel(const __grid_constant__ CUtensorMap tmap_a, const Marlin
   if (nchunks > 0 && warp == MG_WARP_TMA) {
     // ===================== activation TMA producer =====================
     if (lane == 0) {
-      for (int c = 0; c < nchunks; ++c) {
-        const int s = c % NS;
-        const uint32_t use = (uint32_t)(c / NS);
+      // stage / use counters are advanced incrementally: a runtime `c % NS`, `c / NS` costs ~100 cycles of
+      // dependent integer math per stage in these single-thread roles
+      int s = 0;
+      uint32_t use = 0;
+      for (int c = 0; c < nchunks; ++c, s = (s + 1 == NS) ? 0 : s + 1, use += (s == 0)) {
         if (use > 0) mbar_wait_t(&empty[((use - 1) & 1u) * MG_MAX_STAGES + s], ((use - 1) >> 1) & 1u, prof, w0);
         if (p.debug & 4) { mbar_arrive(&full_act[s]); continue; }
         mbar_arrive_expect_tx(&full_act[s], (uint32_t)p.box_rows * 128u);  // TMA always moves the full box
@@ -273,12 +277,13 @@ marlin_w4a16_tc5_kernel(const __grid_constant__ CUtensorMap tmap_a, const Marlin
       const uint32_t fmt = std::is_same<T, __nv_bfloat16>::value ? 1u : 0u;   // 0 = F16, 1 = BF16
       const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n_mma >> 3) << 17) |
                              ((uint32_t)(MG_NT >> 4) << 24);
-      for (int c = 0; c < nchunks; ++c) {
-        const int s = c % NS;
-        const uint32_t par = (uint32_t)(c / NS) & 1u;
-        mbar_wait_t(&full_act[s], par, prof, w0);
+      int s = 0;
+      uint32_t use = 0;
+      for (int c = 0; c < nchunks; ++c, s = (s + 1 == NS) ? 0 : s + 1, use += (s == 0)) {
+        const uint32_t par = use & 1u;
         mbar_wait_t(&full_w[s], par, prof, w1);
         tc_fence_after();
+        const long long tm0 = prof ? clock64() : 0;
         const uint64_t a_desc = make_sw128_desc(smem_u32(w_s + (size_t)s * MG_W_BYTES));
         const uint64_t b_desc = make_sw128_desc(smem_u32(act_s + (size_t)s * p.act_bytes));
 #pragma unroll
@@ -287,10 +292,12 @@ marlin_w4a16_tc5_kernel(const __grid_constant__ CUtensorMap tmap_a, const Marlin
           // advancing 16 k = 32 bytes inside the 128-byte swizzle row = +2 in the descriptor's (addr >> 4) field
           umma_f16(tmem_d, a_desc + (uint64_t)(2 * ks), b_desc + (uint64_t)(2 * ks), idesc, (c > 0 || ks > 0) ? 1u : 0u);
         }
-        umma_commit(&empty[((uint32_t)(c / NS) & 1u) * MG_MAX_STAGES + s]);   // frees act/w stage s when these MMAs retire
+        const long long tm1 = prof ? clock64() : 0;
+        umma_commit(&empty[(use & 1u) * MG_MAX_STAGES + s]);   // frees act/w stage s when these MMAs retire
+        if (prof) { w2 += (unsigned long long)(tm1 - tm0); w3 += (unsigned long long)(clock64() - tm1); }
       }
       umma_commit(accum_full);                   // accumulator complete
-      if (prof) { g_mg_prof[4] = (unsigned long long)(clock64() - t_role0); g_mg_prof[5] = w0; g_mg_prof[6] = w1; }
+      if (prof) { g_mg_prof[4] = (unsigned long long)(clock64() - t_role0); g_mg_prof[5] = w0; g_mg_prof[6] = w1; g_mg_prof[7] = w2; g_mg_prof[16] = w3; }
     }
   } else if (nchunks > 0 && warp < MG_DQ_WARPS) {
     // ===================== dequant warps =====================
@@ -338,7 +345,8 @@ marlin_w4a16_tc5_kernel(const __grid_constant__ CUtensorMap tmap_a, const Marlin
         cp_async16(slot, src);
         if (nblk > 1) cp_async16(slot + 512, src + 128);
         if (grouped) {
-          const int g = p.rows_per_chunk == 2 ? (chunk0 + c) * 2 + (dq >> 1) : (chunk0 + c) / p.chunks_per_group;
+          const int g = p.rows_per_chunk == 2 ? (chunk0 + c) * 2 + (dq >> 1)
+                                             : (p.cpg_shift >= 0 ? (chunk0 + c) >> p.cpg_shift : (chunk0 + c) / p.chunks_per_group);
           const uint8_t* ssrc = reinterpret_cast<const uint8_t*>(p.scales) + ((size_t)g * p.N + n_base + 8 * cq) * 2;
           cp_async16(slot + 1024, ssrc);
           if (nblk > 1) cp_async16(slot + 1536, ssrc + 128);
@@ -354,6 +362,8 @@ marlin_w4a16_tc5_kernel(const __grid_constant__ CUtensorMap tmap_a, const Marlin
 #pragma unroll
     for (int d = 0; d < MG_RING_DEPTH; ++d) prefetch(team + d * MG_TEAMS);
 
+    int s = team % NS;                 // stage and use count of chunk c, advanced by MG_TEAMS per iteration
+    uint32_t use = (uint32_t)(team / NS);
     for (int c = team; c < nchunks; c += MG_TEAMS) {
       cp_async_wait<MG_RING_DEPTH - 1>();           // this lane's copies for chunk c have landed
       const uint32_t slot = ring + (uint32_t)((c / MG_TEAMS) % MG_RING_DEPTH) * MG_SLOT_BYTES;
@@ -376,9 +386,7 @@ marlin_w4a16_tc5_kernel(const __grid_constant__ CUtensorMap tmap_a, const Marlin
           }
         }
       }
-      const int s = c % NS;
-      {
-        const uint32_t use = (uint32_t)(c / NS);          // stage's previous MMAs must have retired
+      {                                                   // stage's previous MMAs must have retired
         if (use > 0) mbar_wait_t(&empty[((use - 1) & 1u) * MG_MAX_STAGES + s], ((use - 1) >> 1) & 1u, prof && warp == 0 && lane == 0, w1);
       }
       const uint32_t wt = w_addr + (uint32_t)s * MG_W_BYTES;
@@ -409,6 +417,8 @@ marlin_w4a16_tc5_kernel(const __grid_constant__ CUtensorMap tmap_a, const Marlin
       __syncwarp();
       if (lane == 0) mbar_arrive(&full_w[s]);
       prefetch(c + MG_RING_DEPTH * MG_TEAMS);     // refill the slot just consumed (its words are in registers)
+      s += MG_TEAMS;
+      while (s >= NS) { s -= NS; ++use; }
     }
     cp_async_wait<0>();
     if (prof && warp == 0 && lane == 0) { g_mg_prof[12] = (unsigned long long)(clock64() - t_role0); g_mg_prof[13] = w0; g_mg_prof[14] = w1; }
@@ -602,6 +612,9 @@ extern "C" int b200_gptq_marlin_gemm(const void* a, const void* b_q_weight, cons
   p.grouped = (gs > 0 && gs < size_k) ? 1 : 0;
   p.rows_per_chunk = (gs > 0 && gs < MG_KC) ? MG_KC / gs : 1;
   p.chunks_per_group = (gs > MG_KC) ? gs / MG_KC : 1;
+  p.cpg_shift = -1;
+  for (int sh = 0; sh < 16; ++sh)
+    if ((1 << sh) == p.chunks_per_group) p.cpg_shift = sh;
   const int chunks = size_k / MG_KC;
   p.chunks_per_split = (chunks + split_k - 1) / split_k;
   cudaStream_t st = (cudaStream_t)stream;

@@ -301,7 +301,9 @@ torch::Tensor gptq_marlin_gemm_impl(torch::Tensor& a, torch::Tensor& b_q_weight,
   TORCH_CHECK((g_idx.size(0) == 0 && perm.size(0) == 0) || (g_idx.size(0) == size_k && perm.size(0) == size_k),
               "Unexpected g_idx.size(0) = ", g_idx.size(0), " and perm.size(0) = ", perm.size(0),
               ", where size_k = ", size_k);
-  TORCH_CHECK(g_idx.size(0) == 0, "act_order (g_idx / perm) is not implemented in the B200 marlin kernel");
+  const bool has_act_order = g_idx.size(0) != 0;
+  TORCH_CHECK(!has_act_order || is_k_full,
+              "act_order with a k-sharded weight (is_k_full = False) is not implemented in the B200 marlin kernel");
   TORCH_CHECK(b_scales.dim() == 2, "b_scales rank = ", b_scales.dim(), " is not 2");
   TORCH_CHECK(b_scales.size(1) == size_n, "b_scales dim 1 = ", b_scales.size(1), " is not size_n = ", size_n);
   const int64_t num_groups = b_scales.size(0);
@@ -332,8 +334,18 @@ torch::Tensor gptq_marlin_gemm_impl(torch::Tensor& a, torch::Tensor& b_q_weight,
     c_tmp_ptr = c_tmp.data_ptr<float>();
   }
   TORCH_CHECK(workspace.scalar_type() == at::kInt, "workspace must be int32");
-  (void)use_fp32_reduce; (void)is_k_full;
-  check(b200_gptq_marlin_gemm(a.data_ptr(), b_q_weight.data_ptr(), b_scales.data_ptr(),
+  (void)use_fp32_reduce;
+  // act-order with the full k range: the checkpoint rows were sorted by group (gptq_marlin_repack with `perm`), so
+  // gathering A's columns with the same permutation reduces the problem to the regular grouped GEMM — what the
+  // reference does with its a_tmp buffer (gptq_marlin.cu:2145-2158, permute_cols_kernel)
+  torch::Tensor a_perm;
+  if (has_act_order) {
+    TORCH_CHECK(perm.scalar_type() == at::kInt, "perm must be int32");
+    a_perm = torch::empty_like(a);
+    check(b200_permute_cols(a.data_ptr(), perm.data_ptr<int>(), a_perm.data_ptr(), size_m, (int)size_k, cur_stream()));
+  }
+  const torch::Tensor& a_used = has_act_order ? a_perm : a;
+  check(b200_gptq_marlin_gemm(a_used.data_ptr(), b_q_weight.data_ptr(), b_scales.data_ptr(),
                               has_zp ? b_zeros.data_ptr() : nullptr, c.data_ptr(), c_tmp_ptr,
                               workspace.data_ptr<int>(), (int)size_m, (int)size_n, (int)size_k, (int)num_groups, (int)type_bits, has_zp ? 1 : 0,
                               dtype_code(a, "gptq_marlin_gemm"), split, cur_stream()));
@@ -366,6 +378,50 @@ void moe_align_block_size(torch::Tensor topk_ids, int64_t num_experts, int64_t b
                                   topk_ids.numel(), (int)num_experts, (int)block_size,
                                   sorted_token_ids.data_ptr<int32_t>(), experts_ids.data_ptr<int32_t>(),
                                   num_tokens_post_pad.data_ptr<int32_t>(), cur_stream()));
+}
+
+torch::Tensor permute_cols(torch::Tensor const& a, torch::Tensor const& perm) {
+  const at::cuda::OptionalCUDAGuard guard(device_of(a));
+  TORCH_CHECK(a.scalar_type() == at::kHalf || a.scalar_type() == at::kBFloat16, "Currently only 16bit types are supported");
+  TORCH_CHECK(a.is_contiguous(), "A must be contiguous");
+  TORCH_CHECK(a.size(-1) % 8 == 0, "A columns must be a multiple of 8 (128bits)");
+  TORCH_CHECK(perm.scalar_type() == at::kInt && perm.numel() == a.size(-1), "perm must be int32 [size_k]");
+  torch::Tensor out = torch::empty_like(a);
+  check(b200_permute_cols(a.data_ptr(), perm.data_ptr<int>(), out.data_ptr(), a.numel() / a.size(-1),
+                          (int)a.size(-1), cur_stream()));
+  return out;
+}
+
+torch::Tensor awq_dequantize(torch::Tensor kernel, torch::Tensor scaling_factors, torch::Tensor zeros,
+                             int64_t split_k_iters, int64_t thx, int64_t thy) {
+  (void)split_k_iters; (void)thx; (void)thy;   // launch-shape hints of the reference kernel; not needed here
+  TORCH_CHECK(kernel.dim() == 2, "awq_dequantize: only 2-D qweight is supported");
+  TORCH_CHECK(scaling_factors.scalar_type() == at::kHalf, "awq_dequantize: scales must be float16");
+  const int64_t in_c = kernel.size(0), qout_c = kernel.size(1);
+  const int64_t G = in_c / scaling_factors.size(0);
+  const at::cuda::OptionalCUDAGuard guard(device_of(scaling_factors));
+  torch::Tensor out = torch::empty({in_c, qout_c * 8}, scaling_factors.options());
+  check(b200_awq_dequantize(kernel.data_ptr(), scaling_factors.data_ptr(), zeros.data_ptr(), out.data_ptr(), in_c,
+                            (int)qout_c, (int)G, cur_stream()));
+  return out;
+}
+
+void advance_step_flashattn(int64_t num_seqs, int64_t num_queries, int64_t block_size, torch::Tensor& input_tokens,
+                            torch::Tensor& sampled_token_ids, torch::Tensor& input_positions,
+                            torch::Tensor& seq_lens, torch::Tensor& slot_mapping, torch::Tensor& block_tables) {
+  TORCH_CHECK(input_tokens.scalar_type() == at::kLong && sampled_token_ids.scalar_type() == at::kLong &&
+              input_positions.scalar_type() == at::kLong && slot_mapping.scalar_type() == at::kLong,
+              "input_tokens / sampled_token_ids / input_positions / slot_mapping must be int64");
+  TORCH_CHECK(seq_lens.scalar_type() == at::kInt && block_tables.scalar_type() == at::kInt,
+              "seq_lens / block_tables must be int32");
+  TORCH_CHECK(input_tokens.size(0) == num_seqs && sampled_token_ids.size(0) == num_queries &&
+              input_positions.size(0) == num_seqs && seq_lens.size(0) == num_seqs &&
+              slot_mapping.size(0) == num_seqs && block_tables.size(0) == num_seqs, "advance_step: bad tensor sizes");
+  const at::cuda::OptionalCUDAGuard guard(device_of(input_tokens));
+  check(b200_advance_step_flashattn((int)num_seqs, (int)num_queries, (int)block_size, input_tokens.data_ptr<int64_t>(),
+                                    sampled_token_ids.data_ptr<int64_t>(), input_positions.data_ptr<int64_t>(),
+                                    seq_lens.data_ptr<int>(), slot_mapping.data_ptr<int64_t>(),
+                                    block_tables.data_ptr<int>(), block_tables.stride(0), cur_stream()));
 }
 
 torch::Tensor gptq_marlin_repack(torch::Tensor& b_q_weight, torch::Tensor& perm, c10::SymInt size_k_s,
@@ -583,6 +639,22 @@ TORCH_LIBRARY(_C, ops) {
       "                     Tensor! experts_ids,"
       "                     Tensor! num_tokens_post_pad) -> ()");
   ops.impl("moe_align_block_size", torch::kCUDA, &moe_align_block_size);
+
+  // prepare_inputs advance_step (kernels/torch_bindings.cpp:77-82)
+  ops.def(
+      "advance_step_flashattn(int num_seqs, int num_queries, int block_size, "
+      "Tensor! input_tokens, Tensor sampled_token_ids, "
+      "Tensor! input_positions, Tensor! seq_lens, Tensor! slot_mapping, "
+      "Tensor block_tables) -> ()");
+  ops.impl("advance_step_flashattn", torch::kCUDA, &advance_step_flashattn);
+
+  // AWQ dequantisation (kernels/torch_bindings.cpp:147-151) and act-order column gather (:218-219)
+  ops.def(
+      "awq_dequantize(Tensor _kernel, Tensor _scaling_factors, "
+      "Tensor _zeros, int split_k_iters, int thx, int thy) -> Tensor");
+  ops.impl("awq_dequantize", torch::kCUDA, &awq_dequantize);
+  ops.def("permute_cols(Tensor A, Tensor perm) -> Tensor");
+  ops.impl("permute_cols", torch::kCUDA, &permute_cols);
 
   // Marlin-format weight-only quantised GEMM + repack (kernels/torch_bindings.cpp:195-215)
   ops.def(

@@ -209,6 +209,18 @@ int b200_car_get_graph_buffer_ipc_meta(int64_t fa, void* handles_out, int64_t* o
 /* handles: [world_size][n] x 64 bytes, offsets: [world_size][n] */
 int b200_car_register_graph_buffers(int64_t fa, const void* handles, const int64_t* offsets, int n);
 
+/* ---- small adjacent ops ------------------------------------------------------------------------------
+ * replaces permute_cols            kernels/permute_cols.cu (schema torch_bindings.cpp:218-219): out[m,k] = a[m,perm[k]]
+ *          awq_dequantize          kernels/quantization/awq/gemm_kernels.cu:720-780 (schema :147-151), fp16 only
+ *          advance_step_flashattn  kernels/prepare_inputs/advance_step.cu:13-52 (schema torch_bindings.cpp:77-82) */
+int b200_permute_cols(const void* a, const int32_t* perm, void* out, int64_t size_m, int size_k, void* stream);
+int b200_awq_dequantize(const void* qweight, const void* scales, const void* zeros, void* out, int64_t in_c,
+                        int qout_c, int group_size, void* stream);
+int b200_advance_step_flashattn(int num_seqs, int num_queries, int block_size, int64_t* input_tokens,
+                                const int64_t* sampled_token_ids, int64_t* input_positions, int32_t* seq_lens,
+                                int64_t* slot_mapping, const int32_t* block_tables, int64_t block_tables_stride,
+                                void* stream);
+
 /* ---- device queries -----------------------------------------------------------------------------
  * replaces get_device_attribute / get_max_shared_memory_per_block_device_attribute
  *          kernels/cuda_utils_kernels.cu (schema torch_bindings.cpp:497-504) */

@@ -205,3 +205,32 @@ def marlin_gemm(a: torch.Tensor, w_ref: torch.Tensor) -> torch.Tensor:
     """C = A . W with W already dequantised to the activation dtype; fp32 accumulation
     (tests/kernels/test_marlin_gemm.py:236-254 compares against `a @ w_ref`)."""
     return (a.float() @ w_ref.float()).to(a.dtype)
+
+
+def marlin_quantize_act_order(w: torch.Tensor, num_bits: int, group_size: int, seed: int = 0):
+    """GPTQ act-order checkpoint (aphrodite/quantization/utils/quant_utils.py:208-240 + :314-331, sort_weights;
+    marlin_utils_test.py:95-125): rows of the quantised matrix are randomly permuted (simulated activation order),
+    g_idx records each row's group, then rows are sorted by group for the kernel.
+    Returns (w_ref [checkpoint row order], marlin_q_w, marlin_scales, g_idx_sorted int32, sort_indices int32)."""
+    K, N = w.shape
+    bias = 1 << (num_bits - 1)
+    w_ref, q_w, s, _ = quantize_weights(w, num_bits, group_size, bias, False)
+    g_idx = (torch.arange(K) // group_size).int()
+    rand_perm = torch.randperm(K, generator=torch.Generator().manual_seed(seed))
+    g_idx, q_w, w_ref = g_idx[rand_perm].contiguous(), q_w[rand_perm].contiguous(), w_ref[rand_perm].contiguous()
+    sort_indices = torch.argsort(g_idx, stable=True).int()
+    q_sorted = q_w[sort_indices.long()].contiguous()
+    return (w_ref, marlin_weights(q_sorted, num_bits), marlin_permute_scales(s, K, N, group_size),
+            g_idx[sort_indices.long()].contiguous(), sort_indices)
+
+
+def awq_dequantize(qweight: torch.Tensor, scales: torch.Tensor, zeros: torch.Tensor) -> torch.Tensor:
+    """kernels/quantization/awq/gemm_kernels.cu:720-780: out[k,n] = fp16((q - z)) * s in fp16 arithmetic."""
+    K, N8 = qweight.shape
+    N = N8 * 8
+    G = K // scales.shape[0]
+    undo = np.argsort(_interleave(4))
+    q = unpack_cols(qweight, 4, K, N).reshape(-1, 8)[:, undo].reshape(K, N)
+    z = unpack_cols(zeros, 4, K // G, N).reshape(-1, 8)[:, undo].reshape(K // G, N)
+    d = (q - z.repeat_interleave(G, dim=0)).to(torch.float16)
+    return (d.float() * scales.repeat_interleave(G, dim=0).float()).to(torch.float16)

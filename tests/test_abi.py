@@ -103,6 +103,20 @@ REF_SCHEMAS = {
     "_moe_C::topk_softmax":
         "topk_softmax(Tensor! topk_weights, Tensor! topk_indices, Tensor! token_expert_indices,"
         " Tensor gating_output) -> ()",
+    "_C::advance_step_flashattn":
+        "advance_step_flashattn(int num_seqs, int num_queries, int block_size, Tensor! input_tokens,"
+        " Tensor sampled_token_ids, Tensor! input_positions, Tensor! seq_lens, Tensor! slot_mapping,"
+        " Tensor block_tables) -> ()",
+    "_C::awq_dequantize":
+        "awq_dequantize(Tensor _kernel, Tensor _scaling_factors, Tensor _zeros, int split_k_iters, int thx,"
+        " int thy) -> Tensor",
+    "_C::permute_cols": "permute_cols(Tensor A, Tensor perm) -> Tensor",
+    "_C_custom_ar::init_custom_ar":
+        "init_custom_ar(Tensor meta, Tensor rank_data, str[] handles, int[] offsets, int rank,"
+        " bool full_nvlink) -> int",
+    "_C_custom_ar::all_reduce_reg": "all_reduce_reg(int fa, Tensor inp, Tensor! out) -> ()",
+    "_C_custom_ar::all_reduce_unreg": "all_reduce_unreg(int fa, Tensor inp, Tensor reg_buffer, Tensor! out) -> ()",
+    "_C_custom_ar::register_buffer": "register_buffer(int fa, Tensor t, str[] handles, int[] offsets) -> ()",
     "_C_cuda_utils::get_device_attribute": "get_device_attribute(int attribute, int device_id) -> int",
     "_C_cuda_utils::get_max_shared_memory_per_block_device_attribute":
         "get_max_shared_memory_per_block_device_attribute(int device_id) -> int",
@@ -123,6 +137,14 @@ def test_torch_ops_registered_with_reference_schema(op):
     ours = packet.default._schema
     ref = torch._C.parse_schema(f"{ns}::{REF_SCHEMAS[op]}")
     assert _sig(ours) == _sig(ref), f"{op}: {ours} != {ref}"
+
+
+def test_custom_ar_inferred_schema_ops_exist():
+    from aphrodite_engine_b200 import _native
+    _native.load_torch_ops()
+    for name in ("dispose", "meta_size", "get_graph_buffer_ipc_meta", "register_graph_buffers"):
+        assert hasattr(torch.ops._C_custom_ar, name)
+    assert torch.ops._C_custom_ar.meta_size() > 0 and torch.ops._C_custom_ar.meta_size() % 128 == 0
 
 
 def test_shim_exports_pyinit_for_import_as_aphrodite_C():

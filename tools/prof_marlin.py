@@ -22,6 +22,6 @@ for M, K, N in ((16, 4096, 28672), (256, 4096, 28672), (16, 14336, 4096), (256, 
     n = max(v[2], 1)
     print(f"M={M} K={K} N={N} chunks={v[2]}  per-chunk cycles:")
     print(f"  act producer : total {v[0]/n:7.0f}  wait_empty {v[1]/n:7.0f}")
-    print(f"  mma issuer   : total {v[4]/n:7.0f}  wait_full_act {v[5]/n:7.0f}  wait_full_w {v[6]/n:7.0f}")
+    print(f"  mma issuer   : total {v[4]/n:7.0f}  wait_full_act {v[5]/n:7.0f}  wait_full_w {v[6]/n:7.0f}  issue4mma {v[7]/n:7.0f}  commit {v[16]/n:7.0f}")
     print(f"  pk producer  : total {v[8]/n:7.0f}  wait_pk_empty {v[9]/n:7.0f}")
     print(f"  dequant w3   : total {v[12]/n:7.0f}  wait_pk_full {v[13]/n:7.0f}  wait_empty {v[14]/n:7.0f}   (+epilogue: {v[15]/n:7.0f})")
