@@ -25,6 +25,8 @@
 #include <float.h>
 #include <math.h>
 
+#include <type_traits>
+
 namespace b200 {
 
 static constexpr float kLog2e = 1.4426950408889634f;
@@ -93,22 +95,34 @@ __device__ __forceinline__ uint32_t movmatrix_trans(uint32_t a) {
   return d;
 }
 
-// 4 packed fp8 -> two packed 16-bit pairs (elements 0,1 and 2,3), scaled
-template <typename T, int KV>
-__device__ __forceinline__ void dequant4(uint32_t w, float scale, uint32_t& lo, uint32_t& hi) {
+// fp8 KV path. Every e4m3 / e5m2 value is exactly representable in fp16 and the conversion is ONE hardware
+// instruction per pair (cvt.rn.f16x2.e4m3x2), so the fp8 contractions run as fp16 MMAs whatever the model dtype:
+// Q is converted to fp16 once per CTA (exact for bf16 values in fp16's normal range), P is packed as fp16, and the
+// per-tensor scales leave the per-element path: k_scale multiplies the logits, v_scale the final output.
+// (The reference materialises T(fp8 * scale) per element, quant_utils.cuh:296-360: identical when the scales are
+// 1.0 — its CPU path supports nothing else — and within the rounding noise of that per-element product otherwise;
+// the first version of this kernel did exactly that and was ALU-bound at 0.74 of the HBM peak.)
+template <int KV>
+__device__ __forceinline__ void fp8x4_to_f16(uint32_t w, uint32_t& lo, uint32_t& hi) {
   constexpr __nv_fp8_interpretation_t interp = (KV == B200_KV_FP8_E5M2) ? __NV_E5M2 : __NV_E4M3;
-  __half2_raw h01 = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)(w & 0xffffu), interp);
-  __half2_raw h23 = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)(w >> 16), interp);
-  float2 f01 = __half22float2(__half2(h01));
-  float2 f23 = __half22float2(__half2(h23));
-  lo = pack2<T>(f01.x * scale, f01.y * scale);
-  hi = pack2<T>(f23.x * scale, f23.y * scale);
+  const __half2_raw h01 = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)(w & 0xffffu), interp);
+  const __half2_raw h23 = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)(w >> 16), interp);
+  lo = (uint32_t)h01.x | ((uint32_t)h01.y << 16);
+  hi = (uint32_t)h23.x | ((uint32_t)h23.y << 16);
+}
+// two 16-bit values of T -> packed fp16 pair
+template <typename T> __device__ __forceinline__ uint32_t pair_to_f16(uint32_t v);
+template <> __device__ __forceinline__ uint32_t pair_to_f16<__half>(uint32_t v) { return v; }
+template <> __device__ __forceinline__ uint32_t pair_to_f16<__nv_bfloat16>(uint32_t v) {
+  const float lo = __uint_as_float(v << 16), hi = __uint_as_float(v & 0xffff0000u);
+  return pack2<__half>(lo, hi);
 }
 
 template <typename T, int D, int BS, int KV, bool PARTITIONED>
 __global__ void __launch_bounds__(kFastThreads, 2)
 paged_attention_tc_kernel(const AttnParams p) {
   using Cfg = FastCfg<D, BS, KV>;
+  using MT = typename std::conditional<KV == B200_KV_AUTO, T, __half>::type;   // tensor-core operand type
   constexpr int NST = Cfg::NSTAGES;
   constexpr int KSTEPS = D / 16;
   constexpr int MTILES = D / 16;
@@ -207,9 +221,13 @@ paged_attention_tc_kernel(const AttnParams p) {
         const int d0 = ks * 16 + kA * q;
         qf[ks][0] = hv ? *reinterpret_cast<const uint32_t*>(qrow + d0) : 0u;
         qf[ks][1] = hv ? *reinterpret_cast<const uint32_t*>(qrow + d0 + kBoff) : 0u;
+        if constexpr (KV != B200_KV_AUTO) {
+          qf[ks][0] = pair_to_f16<T>(qf[ks][0]);
+          qf[ks][1] = pair_to_f16<T>(qf[ks][1]);
+        }
       }
     }
-    const float sc = p.scale * kLog2e;
+    const float sc = p.scale * kLog2e * (KV == B200_KV_AUTO ? 1.f : p.k_scale);
     float alibi[2] = {0.f, 0.f};
     if (p.alibi_slopes != nullptr) {
       if (2 * q < nheads) alibi[0] = p.alibi_slopes[head0 + 2 * q] * kLog2e;
@@ -259,9 +277,9 @@ paged_attention_tc_kernel(const AttnParams p) {
             const uint32_t wA = *reinterpret_cast<const uint32_t*>(kr + (sub * 16 + tokA) * 16);
             const uint32_t wB = *reinterpret_cast<const uint32_t*>(kr + (sub * 16 + tokB) * 16);
             uint32_t a[4];
-            dequant4<T, KV>(wA, p.k_scale, a[0], a[2]);
-            dequant4<T, KV>(wB, p.k_scale, a[1], a[3]);
-            mma_16816<T>(st, a, qf[ks][0], qf[ks][1]);
+            fp8x4_to_f16<KV>(wA, a[0], a[2]);
+            fp8x4_to_f16<KV>(wB, a[1], a[3]);
+            mma_16816<__half>(st, a, qf[ks][0], qf[ks][1]);
           }
         }
 
@@ -301,8 +319,8 @@ paged_attention_tc_kernel(const AttnParams p) {
         l_run[0] += p0 + p2;
         l_run[1] += p1 + p3;
         // P^T B-fragments via in-register 8x8 transposes
-        const uint32_t pb0 = movmatrix_trans(pack2<T>(p0, p1));
-        const uint32_t pb1 = movmatrix_trans(pack2<T>(p2, p3));
+        const uint32_t pb0 = movmatrix_trans(pack2<MT>(p0, p1));
+        const uint32_t pb1 = movmatrix_trans(pack2<MT>(p2, p3));
 
         // ---------------- O^T += V^T . P^T ----------------
         if constexpr (KV == B200_KV_AUTO) {
@@ -335,9 +353,9 @@ paged_attention_tc_kernel(const AttnParams p) {
             const uint32_t wA = *reinterpret_cast<const uint32_t*>(vr) & bmask;
             const uint32_t wB = *reinterpret_cast<const uint32_t*>(vr + 8 * BS) & bmask;
             uint32_t a[4];
-            dequant4<T, KV>(wA, p.v_scale, a[0], a[2]);
-            dequant4<T, KV>(wB, p.v_scale, a[1], a[3]);
-            mma_16816<T>(o[mt], a, pb0, pb1);
+            fp8x4_to_f16<KV>(wA, a[0], a[2]);
+            fp8x4_to_f16<KV>(wB, a[1], a[3]);
+            mma_16816<__half>(o[mt], a, pb0, pb1);
           }
         }
       }
@@ -389,7 +407,8 @@ paged_attention_tc_kernel(const AttnParams p) {
         den += f * merge_l[w * kHeadsPerCta + h];
       }
     }
-    const float val = num * __fdividef(1.f, den + 1e-6f);
+    float val = num * __fdividef(1.f, den + 1e-6f);
+    if (KV != B200_KV_AUTO) val *= p.v_scale;
     const int head = head0 + h;
     if (PARTITIONED) {
       const int64_t base = ((int64_t)seq * p.num_heads + head) * p.max_num_partitions + part;
