@@ -49,6 +49,7 @@ SIGNATURES = {
     "b200_marlin_gemm_plan": [c_int] * 4,
     "b200_debug_marlin_prof": [c_void_p],
     "b200_gptq_marlin_gemm": [c_void_p] * 7 + [c_int] * 8 + [c_void_p],
+    "b200_marlin_gemm_moe": [c_void_p] * 3 + [c_int64] + [c_void_p] * 7 + [c_int] * 10 + [c_void_p],
     "b200_gptq_marlin_repack": [c_void_p] * 3 + [c_int] * 3 + [c_void_p],
     "b200_awq_marlin_repack": [c_void_p] * 2 + [c_int] * 3 + [c_void_p],
     "b200_moe_align_block_size": [c_void_p, c_int, c_int64, c_int, c_int] + [c_void_p] * 4,

@@ -283,7 +283,8 @@ torch::Tensor gptq_marlin_gemm_impl(torch::Tensor& a, torch::Tensor& b_q_weight,
     TORCH_CHECK((type_bits == 4 && type_bias == 8) || (type_bits == 8 && type_bias == 128),
                 "b_q_type must be uint4b8 or uint8b128 when has_zp = False. Got = ", type_str);
   }
-  TORCH_CHECK(!(has_zp && is_zp_float), "float zero points (HQQ) are not implemented in the B200 marlin kernel");
+  if (has_zp && is_zp_float)
+    TORCH_CHECK(a.scalar_type() == at::kHalf, "Computation type must be float16 (half) when using float zero points.");
   const int64_t pack_factor = 32 / type_bits;
   TORCH_CHECK(a.size(0) == size_m, "Shape mismatch: a.size(0) = ", a.size(0), ", size_m = ", size_m);
   TORCH_CHECK(a.size(1) == size_k, "Shape mismatch: a.size(1) = ", a.size(1), ", size_k = ", size_k);
@@ -312,8 +313,14 @@ torch::Tensor gptq_marlin_gemm_impl(torch::Tensor& a, torch::Tensor& b_q_weight,
   if (has_zp) {
     TORCH_CHECK(b_zeros.dim() == 2, "b_zeros rank = ", b_zeros.dim(), " is not 2");
     TORCH_CHECK(b_zeros.size(0) == num_groups, "b_zeros dim 0 = ", b_zeros.size(0), " is not num_groups = ", num_groups);
-    TORCH_CHECK(b_zeros.size(1) == size_n / pack_factor, "b_zeros dim 1 = ", b_zeros.size(1),
-                " is not size_n / pack_factor = ", size_n / pack_factor);
+    if (is_zp_float) {
+      TORCH_CHECK(b_zeros.size(1) == size_n, "b_zeros dim 1 = ", b_zeros.size(1), " is not size_n = ", size_n);
+      TORCH_CHECK(b_zeros.scalar_type() == at::kHalf, "float zero points must be float16");
+    } else {
+      TORCH_CHECK(b_zeros.size(1) == size_n / pack_factor, "b_zeros dim 1 = ", b_zeros.size(1),
+                  " is not size_n / pack_factor = ", size_n / pack_factor);
+    }
+    TORCH_CHECK(b_zeros.device().is_cuda() && b_zeros.is_contiguous(), "b_zeros must be a contiguous GPU tensor");
   }
   TORCH_CHECK(size_n % 64 == 0, "size_n = ", size_n, ", is not divisible by min_thread_n = 64");
   const int64_t min_workspace_size = (size_n / 64) * 16;
@@ -347,7 +354,7 @@ torch::Tensor gptq_marlin_gemm_impl(torch::Tensor& a, torch::Tensor& b_q_weight,
   const torch::Tensor& a_used = has_act_order ? a_perm : a;
   check(b200_gptq_marlin_gemm(a_used.data_ptr(), b_q_weight.data_ptr(), b_scales.data_ptr(),
                               has_zp ? b_zeros.data_ptr() : nullptr, c.data_ptr(), c_tmp_ptr,
-                              workspace.data_ptr<int>(), (int)size_m, (int)size_n, (int)size_k, (int)num_groups, (int)type_bits, has_zp ? 1 : 0,
+                              workspace.data_ptr<int>(), (int)size_m, (int)size_n, (int)size_k, (int)num_groups, (int)type_bits, has_zp ? (is_zp_float ? 2 : 1) : 0,
                               dtype_code(a, "gptq_marlin_gemm"), split, cur_stream()));
   return c;
 }

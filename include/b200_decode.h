@@ -154,13 +154,17 @@ int b200_activation(void* out, const void* input, int num_tokens, int d, int act
  *          gptq_marlin_repack kernels/quantization/gptq_marlin/gptq_marlin_repack.cu:271-343 (schema :204-208)
  *          awq_marlin_repack  kernels/quantization/gptq_marlin/awq_marlin_repack.cu:208-268  (schema :211-215)
  * a [size_m, size_k] f16/bf16 contiguous; b_q_weight int32 [size_k/16, size_n*16/pack] (Marlin tiles);
- * b_scales [num_groups, size_n] (Marlin-permuted, num_groups == 1: channel-wise); b_zeros int32
- * [num_groups, size_n/8] (AWQ integer zero points, Marlin layout) or NULL; c [size_m, size_n].
+ * b_scales [num_groups, size_n] (Marlin-permuted, num_groups == 1: channel-wise); c [size_m, size_n].
+ * num_bits 4 or 8. has_zp: 0 = symmetric codes (uint4b8 / uint8b128, b_zeros NULL), 1 = b_zeros int32
+ * [num_groups, size_n/pack] (AWQ integer zero points, Marlin layout: uint4 / uint8), 2 = b_zeros f16
+ * [num_groups, size_n] (HQQ float zero points, permuted like the scales; float16 only — the reference's
+ * is_zp_float, gptq_marlin.cu:2266-2270).
  * Split-k (b200_marlin_gemm_plan(...) > 1) needs c_tmp: fp32 [split_k, size_m, size_n] scratch (no
  * initialisation; the reference's use_fp32_reduce buffer, gptq_marlin.cu:2313-2327) and `workspace`:
  * int32 [>= size_n/64*16], ZERO on entry and returned to zero (the reference's lock workspace,
  * torch_bindings.cpp:167-176). The last split to arrive sums the partial slabs in a fixed order
- * (deterministic). split_k <= 0 = use the plan. 4-bit only (uint4b8, uint4+zp); act-order (g_idx/perm) is not supported. */
+ * (deterministic). split_k <= 0 = use the plan. Act-order with the full k range is handled by the caller
+ * permuting A's columns (b200_permute_cols), as the reference does with a_tmp (gptq_marlin.cu:2145-2158). */
 int b200_marlin_gemm_plan(int size_m, int size_n, int size_k, int num_groups);
 /* debug only: per-role cycle attribution of the last GEMM launched with B200_MARLIN_DEBUG & 16 (32 x u64) */
 int b200_debug_marlin_prof(unsigned long long* out32);
@@ -168,6 +172,22 @@ int b200_gptq_marlin_gemm(const void* a, const void* b_q_weight, const void* b_s
                           const void* b_zeros, void* c, float* c_tmp, int32_t* workspace,
                           int size_m, int size_n, int size_k, int num_groups, int num_bits,
                           int has_zp, int dtype, int split_k, void* stream);
+/* Grouped (mixture-of-experts) W4A16 GEMM.
+ * replaces marlin_gemm_moe    kernels/moe/marlin_moe_ops.cu:1482-1546 (schema kernels/moe/torch_bindings.cpp:17-23)
+ * a: [size_m, size_k] (replicate_input = 1: row r of the output reads a[r / topk]) or [size_m*topk, size_k];
+ * b_q_weights int32 [E, size_k/16, size_n*2] (uint4b8 Marlin tiles); b_scales [E, num_groups, size_n];
+ * sorted_ids int32 [sorted_capacity]: output of moe_align_block_size(topk_ids, moe_block_size, E) (values >=
+ * size_m*topk are padding); topk_ids int32 [size_m*topk]; topk_weights f32 [size_m*topk]; perm int32 [E, size_k]
+ * act-order column permutation per expert (is_k_full) or NULL; c [size_m*topk, size_n]: row r = a_row(r) . W[expert(r)]
+ * (* topk_weights[r] if apply_weights; rows of tokens routed to no valid expert are left untouched).
+ * Scratch owned by the caller: a_sorted [sorted_capacity, size_k] of dtype, expert_offsets int32 [E + 1].
+ * Launches are stream-ordered and CUDA-graph capturable (no host synchronisation: the grid is an upper bound). */
+int b200_marlin_gemm_moe(const void* a, const void* b_q_weights, const int32_t* sorted_ids,
+                         int64_t sorted_capacity, const float* topk_weights, const int32_t* topk_ids,
+                         const void* b_scales, const int32_t* perm, void* c, void* a_sorted,
+                         int32_t* expert_offsets, int size_m, int size_n, int size_k, int num_groups,
+                         int num_experts, int topk, int moe_block_size, int replicate_input,
+                         int apply_weights, int dtype, void* stream);
 /* b_q_weight: GPTQ int32 [size_k/pack, size_n]; perm: int32 [size_k] act-order sort indices or NULL;
  * out: int32 [size_k/16, size_n*16/pack]. Bit-exact integer re-tiling. num_bits 4 or 8. */
 int b200_gptq_marlin_repack(const void* b_q_weight, const int32_t* perm, void* out, int size_k,

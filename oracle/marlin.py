@@ -234,3 +234,50 @@ def awq_dequantize(qweight: torch.Tensor, scales: torch.Tensor, zeros: torch.Ten
     z = unpack_cols(zeros, 4, K // G, N).reshape(-1, 8)[:, undo].reshape(K // G, N)
     d = (q - z.repeat_interleave(G, dim=0)).to(torch.float16)
     return (d.float() * scales.repeat_interleave(G, dim=0).float()).to(torch.float16)
+
+
+def hqq_marlin_quantize(q_w: torch.Tensor, s: torch.Tensor, zp: torch.Tensor, group_size: int):
+    """HQQ float zero points (aphrodite/quantization/hqq_marlin.py:183-226): codes q [K,N] uint4, fp16 scale / zero
+    [K/g, N]; W = fp16(fp16(q - zero) * scale) — the kernel's sub_zpf + scale chain (gptq_marlin.cu:393-403, 366-379).
+    Returns (w_ref fp16, marlin_q_w, marlin_scales, marlin_zeros): zeros use the SCALE permutation."""
+    K, N = q_w.shape
+    s, zp = s.half(), zp.half()
+    rep = lambda t: t.repeat_interleave(group_size, dim=0)
+    w_ref = (q_w.half() - rep(zp)) * rep(s)
+    return (w_ref, marlin_weights(q_w.int(), 4), marlin_permute_scales(s, K, N, group_size),
+            marlin_permute_scales(zp, K, N, group_size))
+
+
+def marlin_gemm_moe(a: torch.Tensor, w_refs, topk_ids: torch.Tensor, topk_weights: torch.Tensor,
+                    replicate_input: bool, apply_weights: bool) -> torch.Tensor:
+    """kernels/moe/marlin_moe_ops.cu:1482-1546 semantics with dequantised expert weights w_refs[e] [K, N]:
+    row r = t * topk + j of C is a[t] (replicate_input) or a[r] times W[topk_ids[t, j]], rounded to the activation
+    dtype, then optionally multiplied by topk_weights[t, j] in fp32 and rounded again (:945-956).
+    Returns C [M, topk, N]; rows routed to an invalid expert stay zero."""
+    M, topk = topk_ids.shape
+    N = w_refs[0].shape[1]
+    out = torch.zeros(M * topk, N, dtype=a.dtype)
+    flat = topk_ids.reshape(-1).long()
+    rows = torch.arange(M * topk)
+    for e, w in enumerate(w_refs):
+        sel = rows[flat == e]
+        if sel.numel() == 0:
+            continue
+        src = a[sel // topk] if replicate_input else a[sel]
+        o = (src.float() @ w.float()).to(a.dtype)
+        if apply_weights:
+            o = (topk_weights.reshape(-1)[sel].float()[:, None] * o.float()).to(a.dtype)
+        out[sel] = o
+    return out.view(M, topk, N)
+
+
+def fused_marlin_moe(a: torch.Tensor, w1_refs, w2_refs, topk_weights: torch.Tensor,
+                     topk_ids: torch.Tensor) -> torch.Tensor:
+    """aphrodite/modeling/layers/fused_moe/fused_moe.py:529-542: gate_up GEMM, silu_and_mul, down GEMM with the
+    routing weights applied, sum over the topk slots."""
+    from oracle import paged_ops as po
+    M, topk = topk_ids.shape
+    gate_up = marlin_gemm_moe(a, w1_refs, topk_ids, topk_weights, True, False)
+    act = po.silu_and_mul(gate_up.view(M * topk, -1))
+    down = marlin_gemm_moe(act, w2_refs, topk_ids, topk_weights, False, True)
+    return torch.sum(down, dim=1)

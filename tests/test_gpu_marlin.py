@@ -128,3 +128,70 @@ def test_marlin_argument_errors(ops):
     with pytest.raises(RuntimeError, match="workspace.numel"):
         ops.gptq_marlin_gemm(a, mq, ms, empty, empty, empty, torch.zeros(1, dtype=torch.int32, device=DEV),
                              _types().uint4b8, 4, 64, 128, True, False, True, False)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("group_size", [-1, 32, 128])
+@pytest.mark.parametrize("mkn", [(1, 128, 64), (16, 512, 192), (100, 256, 448), (256, 2048, 512), (300, 1024, 256)])
+def test_gptq_marlin_gemm_uint8b128(ops, dtype, group_size, mkn):
+    M, K, N = mkn
+    torch.manual_seed(M * 3 + K + N)
+    a = torch.randn(M, K).to(dtype)
+    w = torch.randn(K, N).to(dtype)
+    w_ref, mq, ms = om.marlin_quantize(w, 8, group_size)
+    empty = torch.empty(0, dtype=torch.int32, device=DEV)
+    out = ops.gptq_marlin_gemm(a.to(DEV), mq.to(DEV), ms.to(DEV), empty, empty, empty, _workspace(N),
+                               _types().uint8b128, M, N, K, True, False, True, False)
+    torch.cuda.synchronize()
+    assert out.shape == (M, N) and out.dtype == dtype
+    _check_gemm(out, om.marlin_gemm(a, w_ref))
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("group_size", [-1, 32, 128])
+@pytest.mark.parametrize("mkn", [(1, 128, 64), (48, 512, 256), (256, 1024, 512), (260, 256, 192)])
+def test_awq_marlin_gemm_uint8_zp(ops, dtype, group_size, mkn):
+    M, K, N = mkn
+    torch.manual_seed(M + K + N + 1)
+    a = torch.randn(M, K).to(dtype)
+    w = torch.randn(K, N).to(dtype)
+    w_ref, mq, ms, mzp = om.awq_marlin_quantize(w, 8, group_size)
+    empty = torch.empty(0, dtype=torch.int32, device=DEV)
+    out = ops.gptq_marlin_gemm(a.to(DEV), mq.to(DEV), ms.to(DEV), mzp.to(DEV), empty, empty, _workspace(N),
+                               _types().uint8, M, N, K, True, True, True, False)
+    torch.cuda.synchronize()
+    _check_gemm(out, om.marlin_gemm(a, w_ref))
+
+
+def test_awq_marlin_gemm_uint4_zp_channelwise(ops):
+    M, K, N = 40, 512, 320
+    torch.manual_seed(5)
+    a = torch.randn(M, K).to(torch.bfloat16)
+    w = torch.randn(K, N).to(torch.bfloat16)
+    w_ref, mq, ms, mzp = om.awq_marlin_quantize(w, 4, -1)
+    empty = torch.empty(0, dtype=torch.int32, device=DEV)
+    out = ops.gptq_marlin_gemm(a.to(DEV), mq.to(DEV), ms.to(DEV), mzp.to(DEV), empty, empty, _workspace(N),
+                               _types().uint4, M, N, K, True, True, True, False)
+    torch.cuda.synchronize()
+    _check_gemm(out, om.marlin_gemm(a, w_ref))
+
+
+@pytest.mark.parametrize("group_size", [64, 128])
+@pytest.mark.parametrize("mkn", [(1, 128, 64), (33, 512, 192), (256, 1024, 512)])
+def test_hqq_marlin_gemm_float_zero_points(ops, group_size, mkn):
+    """is_zp_float = True (HQQ): fp16 zero points laid out like the scales; W = fp16(fp16(q - zp) * s)."""
+    M, K, N = mkn
+    g = torch.Generator().manual_seed(M + K + N)
+    a = torch.randn(M, K, generator=g).half()
+    q = torch.randint(0, 16, (K, N), generator=g)
+    s = (torch.rand(K // group_size, N, generator=g) * 0.02 + 0.005).half()
+    zp = (torch.rand(K // group_size, N, generator=g) * 4 + 6).half()
+    w_ref, mq, ms, mz = om.hqq_marlin_quantize(q, s, zp, group_size)
+    empty = torch.empty(0, dtype=torch.int32, device=DEV)
+    out = ops.gptq_marlin_gemm(a.to(DEV), mq.to(DEV), ms.to(DEV), mz.to(DEV), empty, empty, _workspace(N),
+                               _types().uint4, M, N, K, True, True, False, True)
+    torch.cuda.synchronize()
+    _check_gemm(out, om.marlin_gemm(a, w_ref))
+    with pytest.raises(RuntimeError, match="Computation type must be float16"):
+        ops.gptq_marlin_gemm(a.to(DEV).bfloat16(), mq.to(DEV), ms.to(DEV).bfloat16(), mz.to(DEV), empty, empty,
+                             _workspace(N), _types().uint4, M, N, K, True, True, False, True)
