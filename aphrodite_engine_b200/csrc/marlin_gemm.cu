@@ -25,6 +25,7 @@
 //   * epilogue        : the dequant warps tcgen05.ld their TMEM lane quadrant (lane = channel, column = token),
 //                       convert and store C (or red.add into the fp32 split-k buffer).
 #include "common.cuh"
+#include "marlin_dq.cuh"
 
 #include <cuda.h>
 
@@ -47,9 +48,6 @@ static constexpr int MG_THREADS = (MG_DQ_WARPS + 2) * 32;
 static constexpr int MG_W_BYTES = MG_NT * 128;        // 16 KB dequantised weight tile
 static constexpr int MG_RING_DEPTH = 2;               // chunks in flight per warp (x 4 teams = 8 chunks ahead)
 static constexpr int MG_SMEM_TOTAL = 226 * 1024;      // opt-in dynamic shared memory available to one CTA
-
-// zero-point flavours (C ABI `has_zp`): none (symmetric bias 8 / 128), packed integers (AWQ), 16-bit floats (HQQ)
-enum { ZP_NONE = 0, ZP_INT = 1, ZP_FLOAT = 2 };
 
 // per-warp cp.async ring slot: packed words of 2 Marlin blocks | 2 x 512 B scale vectors | zero points
 //   words: 4-bit 2 x 512 B (one uint4 per lane and block), 8-bit 2 x 1024 B (two uint4 per lane and block)
@@ -150,41 +148,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// explicit shared-state-space accesses: the 1024-B re-aligned dynamic smem pointer is a GENERIC pointer to
-// the compiler (it would emit LD.E/ST.E through the generic path, which showed up as long-scoreboard stalls)
-__device__ __forceinline__ uint4 lds128(uint32_t a) {
-  uint4 v;
-  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
-  return v;
-}
-__device__ __forceinline__ uint32_t lds32(uint32_t a) {
-  uint32_t v;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
-  return v;
-}
-__device__ __forceinline__ uint4 ldg_stream128(const void* g) {    // read-once data: no L1 allocation
-  uint4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(g));
-  return v;
-}
-__device__ __forceinline__ void cp_async16(uint32_t saddr, const void* g) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
-}
-__device__ __forceinline__ void cp_async8(uint32_t saddr, const void* g) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(saddr), "l"(g) : "memory");
-}
-__device__ __forceinline__ void cp_async4(uint32_t saddr, const void* g) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(saddr), "l"(g) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) {
-  asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
-}
-
 // debug-only cycle attribution (B200_MARLIN_DEBUG & 16): CTA (0,0,0) accumulates, per role, the cycles spent
 // in each mbarrier wait; read back with b200_debug_marlin_prof()
 __device__ unsigned long long g_mg_prof[32];
@@ -201,101 +164,6 @@ __device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, bool
 __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
          (2ull << 61);
-}
-
-template <typename T> struct DQ;  // magic numbers of the int4 -> 16-bit float trick (exact integers)
-template <> struct DQ<__nv_bfloat16> {
-  static constexpr uint32_t MAGIC = 0x43004300u;          // 128.0 | 128.0 : 128 + q is exact (q < 128)
-  static __device__ __forceinline__ uint32_t offset(int q) {  // bf16x2 of (128 + q)
-    const uint32_t h = 0x4300u + (uint32_t)q;                 // 128+q: mantissa lsb = 1 in [128,256)
-    return h | (h << 16);
-  }
-  static __device__ __forceinline__ uint32_t sub_mul(uint32_t x, uint32_t off, uint32_t s2) {
-    __nv_bfloat162 v = __hsub2(*reinterpret_cast<__nv_bfloat162*>(&x), *reinterpret_cast<__nv_bfloat162*>(&off));
-    v = __hmul2(v, *reinterpret_cast<__nv_bfloat162*>(&s2));
-    return *reinterpret_cast<uint32_t*>(&v);
-  }
-};
-template <> struct DQ<__half> {
-  static constexpr uint32_t MAGIC = 0x64006400u;          // 1024.0 | 1024.0
-  static __device__ __forceinline__ uint32_t offset(int q) {
-    const uint32_t h = 0x6400u + (uint32_t)q;                 // 1024+q exact
-    return h | (h << 16);
-  }
-  static __device__ __forceinline__ uint32_t sub_mul(uint32_t x, uint32_t off, uint32_t s2) {
-    __half2 v = __hsub2(*reinterpret_cast<__half2*>(&x), *reinterpret_cast<__half2*>(&off));
-    v = __hmul2(v, *reinterpret_cast<__half2*>(&s2));
-    return *reinterpret_cast<uint32_t*>(&v);
-  }
-};
-
-__device__ __forceinline__ uint32_t lop3_and_or(uint32_t a, uint32_t b, uint32_t c) {  // (a & b) | c
-  uint32_t r;
-  asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
-  return r;
-}
-
-__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
-  uint32_t r;
-  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
-  return r;
-}
-
-// Weight-code -> 16-bit float pairs, generalised over the code width and the zero-point flavour. All variants
-// produce (q - z) EXACTLY (|q - z| <= 255 fits the 8 significant bits of bf16 and the 11 of fp16) and then round
-// once in the multiply by the scale — the arithmetic of the reference's dequant<> + sub_zp + scale chain
-// (gptq_marlin.cu:156-360, 382-392, 366-379). With float zero points (HQQ) the subtraction rounds too, as there
-// (sub_zpf, :393-403).
-//   offset word `off` per output column: 4-bit / fp16-8-bit: 16-bit pair of MAGIC + z; bf16-8-bit: fp32 bits of
-//   2^23 + z; float zero points: the 16-bit pair {zp, zp}.
-template <typename T, int BITS, int ZP> struct WDQ {
-  static __device__ __forceinline__ uint32_t offset_of(int z) {
-    if constexpr (BITS == 8 && std::is_same<T, __nv_bfloat16>::value) return __float_as_uint(8388608.f + (float)z);
-    else return DQ<T>::offset(z);
-  }
-  static __device__ __forceinline__ uint32_t finish(uint32_t x, uint32_t off, uint32_t s2) {  // x = MAGIC + q pair
-    if constexpr (ZP == ZP_FLOAT) {
-      const uint32_t magic = DQ<T>::MAGIC;
-      __half2 v = __hsub2(*reinterpret_cast<__half2*>(&x), *reinterpret_cast<const __half2*>(&magic));
-      v = __hsub2(v, *reinterpret_cast<__half2*>(&off));
-      v = __hmul2(v, *reinterpret_cast<__half2*>(&s2));
-      return *reinterpret_cast<uint32_t*>(&v);
-    } else {
-      return DQ<T>::sub_mul(x, off, s2);
-    }
-  }
-  // 8-bit: bytes (lo, lo + 2) of `w` are the codes of k and k + 1
-  static __device__ __forceinline__ uint32_t pair8(uint32_t w, int lo, uint32_t off, uint32_t s2) {
-    if constexpr (std::is_same<T, __nv_bfloat16>::value) {
-      const float base = __uint_as_float(off);                       // 2^23 + z
-      const float f0 = __uint_as_float(prmt(w, 0x4B000000u, lo ? 0x7651u : 0x7650u)) - base;
-      const float f1 = __uint_as_float(prmt(w, 0x4B000000u, lo ? 0x7653u : 0x7652u)) - base;
-      uint32_t x = prmt(__float_as_uint(f0), __float_as_uint(f1), 0x7632u);   // exact: |q - z| <= 255
-      __nv_bfloat162 v = __hmul2(*reinterpret_cast<__nv_bfloat162*>(&x), *reinterpret_cast<__nv_bfloat162*>(&s2));
-      return *reinterpret_cast<uint32_t*>(&v);
-    } else {
-      const uint32_t x = prmt(w, 0x64646464u, lo ? 0x5351u : 0x5250u);        // fp16 pair of 1024 + q
-      return finish(x, off, s2);
-    }
-  }
-};
-
-// zero point of column e (= 2j + b) of a lane's 8 columns inside its packed zero-point word(s)
-// (marlin_zero_points: aphrodite/quantization/utils/marlin_utils.py:198-217 — scale permutation, then the
-// interleave [0,2,4,6,1,3,5,7] (4-bit) / [0,2,1,3] (8-bit) inside every int32)
-template <int BITS> __device__ __forceinline__ int zp_code(int e, uint32_t z0, uint32_t z1) {
-  if constexpr (BITS == 4) return (int)((z0 >> (4 * (((e & 1) << 2) | (e >> 1)))) & 0xFu);
-  else {
-    const int r = e & 3;
-    return (int)((((e >> 2) ? z1 : z0) >> (8 * (((r & 1) << 1) | (r >> 1)))) & 0xFFu);
-  }
-}
-
-// position of output column n (0..N) inside a Marlin-permuted scale row
-// (aphrodite/quantization/utils/marlin_utils.py:172-196)
-__device__ __forceinline__ int scale_pos(int n, bool grouped) {
-  if (grouped) return (n & ~63) + 8 * (n & 7) + ((n & 63) >> 3);
-  return (n & ~31) + 8 * ((n & 7) >> 1) + 2 * ((n & 31) >> 3) + (n & 1);
 }
 
 // RING = true : packed words / scales / zero points travel global -> per-warp cp.async ring -> registers
@@ -913,6 +781,21 @@ static void fill_group_params(MarlinParams& p, int size_k, int gs) {
   p.debug = dbg ? atoi(dbg) : 0;
 }
 
+// small-batch mma.sync kernel (marlin_gemm_small.cu)
+int marlin_small_plan(int M, int N, int K, int group_size);
+int marlin_small_gemm(const void* a, const void* b_q, const void* scales, const void* zeros, void* c, float* c_tmp,
+                      int* locks, int M, int N, int K, int num_groups, int has_zp, int dtype, int split_k,
+                      cudaStream_t st);
+static constexpr int MG_SMALL_M = 32;
+static bool marlin_use_small() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200_MARLIN_SMALL");
+    v = e ? (atoi(e) != 0) : 1;
+  }
+  return v != 0;
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -923,10 +806,13 @@ extern "C" int b200_debug_marlin_prof(unsigned long long* out32) {
   return 0;
 }
 
+// upper bound of the number of fp32 partial slabs [M, N] the GEMM may use for this shape (sizes c_tmp)
 extern "C" int b200_marlin_gemm_plan(int size_m, int size_n, int size_k, int num_groups) {
   const int gs = num_groups > 1 ? size_k / num_groups : -1;
   if (size_m <= 0 || size_n <= 0 || size_k < MG_KC) return 1;
-  return plan_split_k(size_m, size_n, size_k, gs);
+  int split = plan_split_k(size_m, size_n, size_k, gs);
+  if (size_m <= MG_SMALL_M) split = std::max(split, marlin_small_plan(size_m, size_n, size_k, gs));
+  return split;
 }
 
 extern "C" int b200_gptq_marlin_gemm(const void* a, const void* b_q_weight, const void* b_scales,
@@ -948,6 +834,9 @@ extern "C" int b200_gptq_marlin_gemm(const void* a, const void* b_q_weight, cons
   B200_CHECK((reinterpret_cast<uintptr_t>(a) & 15) == 0 && (reinterpret_cast<uintptr_t>(b_q_weight) & 15) == 0,
              "a and b_q_weight must be 16-byte aligned");
   if (size_m == 0) return 0;
+  if (num_bits == 4 && has_zp != ZP_FLOAT && size_m <= MG_SMALL_M && marlin_use_small())
+    return marlin_small_gemm(a, b_q_weight, b_scales, b_zeros, c, c_tmp, workspace, size_m, size_n, size_k, num_groups,
+                             has_zp, dtype, split_k, (cudaStream_t)stream);
   if (split_k <= 0) split_k = plan_split_k(size_m, size_n, size_k, gs);
   B200_CHECK(split_k == 1 || (c_tmp != nullptr && workspace != nullptr),
              "split-k needs the fp32 partial buffer [split_k, M, N] and the zeroed lock workspace");

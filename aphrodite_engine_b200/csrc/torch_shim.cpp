@@ -355,7 +355,7 @@ torch::Tensor gptq_marlin_gemm_impl(torch::Tensor& a, torch::Tensor& b_q_weight,
   check(b200_gptq_marlin_gemm(a_used.data_ptr(), b_q_weight.data_ptr(), b_scales.data_ptr(),
                               has_zp ? b_zeros.data_ptr() : nullptr, c.data_ptr(), c_tmp_ptr,
                               workspace.data_ptr<int>(), (int)size_m, (int)size_n, (int)size_k, (int)num_groups, (int)type_bits, has_zp ? (is_zp_float ? 2 : 1) : 0,
-                              dtype_code(a, "gptq_marlin_gemm"), split, cur_stream()));
+                              dtype_code(a, "gptq_marlin_gemm"), /*split_k=*/0, cur_stream()));
   return c;
 }
 

@@ -150,6 +150,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=12)
     ap.add_argument("--only", default="")
+    ap.add_argument("--ms", type=int, nargs="+", default=[256, 16], help="token counts of the marlin GEMM legs")
     a = ap.parse_args()
     so = os.path.join(ROOT, "oracle", "_ref", "_ref_cuda_C.so")
     if not os.path.exists(so):
@@ -162,7 +163,7 @@ def main():
     if want("small"):
         bench_small_ops(ref, a.iters, flush)
     if want("marlin"):
-        bench_marlin(ref, a.iters, flush, (256, 16))
+        bench_marlin(ref, a.iters, flush, a.ms)
     if want("moe"):
         bench_moe(ref, a.iters, flush)
     if want("attn"):
