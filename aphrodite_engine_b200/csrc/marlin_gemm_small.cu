@@ -13,9 +13,12 @@
 //     tcgen05 kernel and to the reference's w_ref), results ARE the mma.sync.m16n8k16 B fragments (registers);
 //     A fragments come from the activation slice with ldmatrix.x4 (swizzled 16-byte pieces, conflict-free);
 //   * fp32 accumulators in registers; the four k-interleaved warps of a block are summed through shared memory;
-//   * k is split across CTAs to fill the SMs; partial tiles go to fp32 slabs and the LAST CTA of a tile (atomic
-//     ticket on the reference's zeroed `workspace`, returned to zero) adds them in split order: deterministic,
-//     no spinning, no co-residency requirement.
+//   * work = (128-channel tile, 64-k chunk) units in tile-major order, cut into gridDim.x EQUAL contiguous ranges
+//     (stream-k): every CTA runs the same number of chunks whatever N / 128 is (224 tiles on 148 SMs would otherwise
+//     quantise to waves). A CTA's range crosses at most a few tiles; each (tile, range) segment is reduced over the
+//     four k-lanes through shared memory; tiles covered by several CTAs go to fp32 slabs [segment][M][N] and the LAST
+//     CTA of a tile (atomic ticket on the reference's zeroed `workspace`, returned to zero) adds them in segment
+//     order: deterministic, no spinning, no co-residency requirement, CUDA-graph capturable.
 #include "common.cuh"
 #include "marlin_dq.cuh"
 
@@ -40,8 +43,8 @@ struct SmallParams {
   int grouped;              // 1: one scale row per k-group
   int ktiles_per_group;     // group_size / 16 (grouped)
   int kpg_shift;            // log2(ktiles_per_group) when a power of two, else -1
-  int ktiles_per_split;
-  int split_k;
+  int chunks;               // K / 64
+  int tiles;                // ceil(N / 128)
 };
 
 template <int MB> struct SmallCfg {
@@ -67,13 +70,25 @@ marlin_w4a16_small_kernel(const SmallParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nb = warp & 1, kq = warp >> 1;
   const int m = lane & 3, cq = lane >> 2;
-  const int n_base = blockIdx.x * 128;
-  const int nblk = min(2, (p.N - n_base) / 64);
-  const int total_kt = p.K / 16;
-  const int kt0 = blockIdx.y * p.ktiles_per_split;
-  const int kt1 = min(total_kt, kt0 + p.ktiles_per_split);
   const T* sc = reinterpret_cast<const T*>(p.scales);
   const T* a = reinterpret_cast<const T*>(p.a);
+  T* cptr = reinterpret_cast<T*>(p.c);
+  __shared__ int s_last;
+
+  // this CTA's contiguous range of (tile, chunk) units
+  const long long U = (long long)p.tiles * p.chunks;
+  const long long G = gridDim.x;
+  const long long u_end = (long long)(blockIdx.x + 1) * U / G;
+  auto cta_of = [&](long long u) { return (int)(((u + 1) * G - 1) / U); };   // owner of unit u
+
+  for (long long u = (long long)blockIdx.x * U / G; u < u_end;) {
+  const int tile = (int)(u / p.chunks);
+  const int cb = (int)(u - (long long)tile * p.chunks);
+  const int ce = (int)min((long long)p.chunks, cb + (u_end - u));
+  u += ce - cb;
+  const int n_base = tile * 128;
+  const int nblk = min(2, (p.N - n_base) / 64);
+  const int kt0 = cb * 4, kt1 = ce * 4;
 
   float acc[MB][8][4];
 #pragma unroll
@@ -212,8 +227,10 @@ marlin_w4a16_small_kernel(const SmallParams p) {
   }
   __syncthreads();
   const int nvalid = min(128, p.N - n_base);
-  T* cptr = reinterpret_cast<T*>(p.c);
-  float* slab = p.split_k > 1 ? p.c_tmp + (size_t)blockIdx.y * p.M * p.N : nullptr;
+  // segments of this tile: one per CTA whose range intersects it (consecutive CTAs)
+  const int cf = cta_of((long long)tile * p.chunks);
+  const int nseg = cta_of((long long)tile * p.chunks + p.chunks - 1) - cf + 1;
+  float* slab = nseg > 1 ? p.c_tmp + (size_t)((int)blockIdx.x - cf) * p.M * p.N : nullptr;
   // thread -> (row, 4 channels): 32 threads cover a row of 128 channels
   for (int r = warp; r < p.M && r < ROWS; r += SM_WARPS) {
     const int ch = lane * 4;
@@ -236,11 +253,10 @@ marlin_w4a16_small_kernel(const SmallParams p) {
     }
   }
   if (slab != nullptr) {
-    // ticket: the last CTA of this channel tile adds the slabs in split order (threadFenceReduction pattern)
-    __shared__ int s_last;
+    // ticket: the last CTA through adds the tile's slabs in segment order (threadFenceReduction pattern)
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(p.locks + blockIdx.x, 1) == p.split_k - 1);
+    if (threadIdx.x == 0) s_last = (atomicAdd(p.locks + tile, 1) == nseg - 1);
     __syncthreads();
     if (s_last) {
       __threadfence();
@@ -249,7 +265,7 @@ marlin_w4a16_small_kernel(const SmallParams p) {
         if (ch < nvalid) {
           const size_t off = (size_t)r * p.N + n_base + ch;
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          for (int z = 0; z < p.split_k; ++z) {
+          for (int z = 0; z < nseg; ++z) {
             const float4 t = __ldcg(reinterpret_cast<const float4*>(p.c_tmp + (size_t)z * p.M * p.N + off));
             v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
           }
@@ -259,33 +275,36 @@ marlin_w4a16_small_kernel(const SmallParams p) {
           *reinterpret_cast<uint2*>(cptr + off) = o;
         }
       }
-      if (threadIdx.x == 0) p.locks[blockIdx.x] = 0;
+      if (threadIdx.x == 0) p.locks[tile] = 0;
     }
   }
+  __syncthreads();                                            // the reduce buffer becomes the rings of the next segment
+  }  // segments
 }
 
-// k split for the small-batch kernel: fill the SMs (2 CTAs per SM share an SM's issue slots, so throughput-wise a
-// wave is num_sms CTAs) while paying for the fp32 partial slabs
-int marlin_small_plan(int M, int N, int K, int group_size) {
-  const int tiles = (N + 127) / 128;
-  const int chunks = K / 64;                       // split granularity: 4 k-tiles (one per k-interleaved warp)
-  const int sms = num_sms();
-  const int gchunks = group_size > 64 ? group_size / 64 : 1;
-  int best = 1;
-  double best_cost = 1e30;
-  for (int split = 1; split <= 16 && split <= chunks; ++split) {
-    int per = (chunks + split - 1) / split;
-    per = (per + gchunks - 1) / gchunks * gchunks;                       // keep splits on group boundaries
-    if ((split - 1) * per >= chunks) continue;                           // an empty last split
-    const int waves = (tiles * split + sms - 1) / sms;
-    const double cost = (double)waves * (per + 1.0) + (split > 1 ? split * (M / 32.0 + 0.25) : 0.0);
-    if (cost < best_cost - 1e-9) { best_cost = cost; best = split; }
+// stream-k launch shape of the small-batch kernel: number of CTAs (2 per SM, at least 8 chunks each) and the largest
+// number of CTAs any tile is spread over (= fp32 slabs the caller must provide; 1 = none)
+static void small_partition(int N, int K, int* grid_out, int* slabs_out) {
+  const long long tiles = (N + 127) / 128, chunks = K / 64, U = tiles * chunks;
+  long long G = std::min<long long>(2LL * num_sms(), std::max<long long>(1, U / 8));
+  int slabs = 1;
+  for (long long t = 0; t < tiles; ++t) {
+    const long long cf = ((t * chunks + 1) * G - 1) / U, cl = ((t * chunks + chunks) * G - 1) / U;
+    slabs = std::max<int>(slabs, (int)(cl - cf + 1));
   }
-  return best;
+  *grid_out = (int)G;
+  *slabs_out = slabs;
+}
+
+int marlin_small_plan(int M, int N, int K, int group_size) {
+  (void)M; (void)group_size;
+  int grid, slabs;
+  small_partition(N, K, &grid, &slabs);
+  return slabs;
 }
 
 template <typename T, int ZP, int MB>
-static int launch_small(const SmallParams& p, cudaStream_t st) {
+static int launch_small(const SmallParams& p, int grid, cudaStream_t st) {
   using Cfg = SmallCfg<MB>;
   auto kern = marlin_w4a16_small_kernel<T, ZP, MB>;
   static thread_local uint64_t attr_done = 0;
@@ -295,12 +314,11 @@ static int launch_small(const SmallParams& p, cudaStream_t st) {
     B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     attr_done |= 1ull << (dev & 63);
   }
-  dim3 grid((p.N + 127) / 128, p.split_k);
   kern<<<grid, SM_THREADS, Cfg::SMEM, st>>>(p);
   return check_launch("marlin_w4a16_small_kernel");
 }
 
-// called by b200_gptq_marlin_gemm for 4-bit weights with M <= 32 (split_k from marlin_small_plan unless > 0)
+// called by b200_gptq_marlin_gemm for 4-bit weights with M <= 32
 int marlin_small_gemm(const void* a, const void* b_q, const void* scales, const void* zeros, void* c, float* c_tmp,
                       int* locks, int M, int N, int K, int num_groups, int has_zp, int dtype, int split_k,
                       cudaStream_t st) {
@@ -313,18 +331,15 @@ int marlin_small_gemm(const void* a, const void* b_q, const void* scales, const 
   p.kpg_shift = -1;
   for (int sh = 0; sh < 16; ++sh)
     if ((1 << sh) == p.ktiles_per_group) p.kpg_shift = sh;
-  if (split_k <= 0) split_k = marlin_small_plan(M, N, K, gs);
-  const int chunks = K / 64;
-  const int gchunks = gs > 64 ? gs / 64 : 1;
-  int per = (chunks + split_k - 1) / split_k;
-  per = (per + gchunks - 1) / gchunks * gchunks;
-  while (split_k > 1 && (split_k - 1) * per >= chunks) --split_k;
-  B200_CHECK(split_k == 1 || (c_tmp != nullptr && locks != nullptr),
-             "split-k needs the fp32 partial buffer [split_k, M, N] and the zeroed lock workspace");
-  p.split_k = split_k;
-  p.ktiles_per_split = per * 4;
+  (void)split_k;                                    // the partition is a pure function of (N, K, SM count)
+  int grid, slabs;
+  small_partition(N, K, &grid, &slabs);
+  B200_CHECK(slabs == 1 || (c_tmp != nullptr && locks != nullptr),
+             "the small-batch kernel needs the fp32 partial buffer [b200_marlin_gemm_plan(), M, N] and the zeroed lock workspace");
+  p.chunks = K / 64;
+  p.tiles = (N + 127) / 128;
   const bool bf = dtype == B200_BF16;
-#define B200_SM(TT, ZZ, MM) return launch_small<TT, ZZ, MM>(p, st)
+#define B200_SM(TT, ZZ, MM) return launch_small<TT, ZZ, MM>(p, grid, st)
   if (M <= 16) {
     if (bf) { if (has_zp) B200_SM(__nv_bfloat16, ZP_INT, 1); B200_SM(__nv_bfloat16, ZP_NONE, 1); }
     if (has_zp) B200_SM(__half, ZP_INT, 1);
