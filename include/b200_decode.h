@@ -159,11 +159,13 @@ int b200_activation(void* out, const void* input, int num_tokens, int d, int act
  * [num_groups, size_n/pack] (AWQ integer zero points, Marlin layout: uint4 / uint8), 2 = b_zeros f16
  * [num_groups, size_n] (HQQ float zero points, permuted like the scales; float16 only — the reference's
  * is_zp_float, gptq_marlin.cu:2266-2270).
- * Split-k (b200_marlin_gemm_plan(...) > 1) needs c_tmp: fp32 [split_k, size_m, size_n] scratch (no
+ * b200_marlin_gemm_plan(...) returns an UPPER BOUND of the number of fp32 partial slabs the GEMM may use for a
+ * shape; when it is > 1 the caller provides c_tmp: fp32 [plan, size_m, size_n] scratch (no
  * initialisation; the reference's use_fp32_reduce buffer, gptq_marlin.cu:2313-2327) and `workspace`:
  * int32 [>= size_n/64*16], ZERO on entry and returned to zero (the reference's lock workspace,
- * torch_bindings.cpp:167-176). The last split to arrive sums the partial slabs in a fixed order
- * (deterministic). split_k <= 0 = use the plan. Act-order with the full k range is handled by the caller
+ * torch_bindings.cpp:167-176). Partial slabs are summed in a fixed order (deterministic). split_k <= 0 = choose
+ * internally (what the torch op does); size_m <= 32 with 4-bit codes runs the streaming kernel, whose stream-k
+ * partition ignores split_k. Act-order with the full k range is handled by the caller
  * permuting A's columns (b200_permute_cols), as the reference does with a_tmp (gptq_marlin.cu:2145-2158). */
 int b200_marlin_gemm_plan(int size_m, int size_n, int size_k, int num_groups);
 /* debug only: per-role cycle attribution of the last GEMM launched with B200_MARLIN_DEBUG & 16 (32 x u64) */

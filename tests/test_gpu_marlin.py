@@ -195,3 +195,72 @@ def test_hqq_marlin_gemm_float_zero_points(ops, group_size, mkn):
     with pytest.raises(RuntimeError, match="Computation type must be float16"):
         ops.gptq_marlin_gemm(a.to(DEV).bfloat16(), mq.to(DEV), ms.to(DEV).bfloat16(), mz.to(DEV), empty, empty,
                              _workspace(N), _types().uint4, M, N, K, True, True, False, True)
+
+
+@pytest.mark.parametrize("mkn", [(16, 4096, 6144), (32, 14336, 4096), (5, 1024, 28672)])
+def test_small_batch_kernel_stream_k_is_deterministic_and_resets_locks(ops, cabi, mkn):
+    """M <= 32 takes the mma.sync streaming kernel: tiles shared by several CTAs are reduced through fp32 slabs and
+    a ticket on the lock workspace — the result must not depend on CTA arrival order and the workspace must return
+    to zero (the reference's workspace contract, kernels/torch_bindings.cpp:167-176)."""
+    M, K, N = mkn
+    torch.manual_seed(K + N)
+    a = (torch.randn(M, K) * 0.5).to(torch.bfloat16)
+    w = torch.randn(K, N).to(torch.bfloat16)
+    w_ref, mq, ms = om.marlin_quantize(w, 4, 128)
+    empty = torch.empty(0, dtype=torch.int32, device=DEV)
+    ws = _workspace(N)
+    ad, mqd, msd = a.to(DEV), mq.to(DEV), ms.to(DEV)
+    outs = [ops.gptq_marlin_gemm(ad, mqd, msd, empty, empty, empty, ws, _types().uint4b8, M, N, K, True, False, True, False)
+            for _ in range(4)]
+    torch.cuda.synchronize()
+    _check_gemm(outs[0], om.marlin_gemm(a, w_ref))
+    assert (ws == 0).all(), "the lock workspace must be returned to zero"
+    for o in outs[1:]:
+        assert torch.equal(outs[0], o), "slab reduce must be deterministic"
+    assert cabi.b200_marlin_gemm_plan(M, N, K, K // 128) >= 1
+
+
+def test_marlin_ops_are_cuda_graph_capturable(ops):
+    """Decode runs under torch.cuda.graph (worker/model_runner.py:1682+): the quantised GEMMs (both kernels) and the
+    grouped MoE GEMM must not synchronise or allocate outside torch's graph-aware allocator."""
+    from aphrodite_engine_b200 import fused_moe as fm
+    torch.manual_seed(1)
+    K, N, E, topk = 512, 256, 4, 2
+    w = torch.randn(K, N).half()
+    w_ref, mq, ms = om.marlin_quantize(w, 4, 128)
+    mqd, msd = mq.to(DEV), ms.to(DEV)
+    empty = torch.empty(0, dtype=torch.int32, device=DEV)
+    ws = _workspace(N)
+    a_small = torch.randn(8, K, dtype=torch.float16, device=DEV)
+    a_big = torch.randn(200, K, dtype=torch.float16, device=DEV)
+    qs, ss, refs = [], [], []
+    for e in range(E):
+        r, q, s = om.marlin_quantize((torch.randn(K, N) * 0.1).half(), 4, 128)
+        refs.append(r); qs.append(q); ss.append(s)
+    q3, s3 = torch.stack(qs).to(DEV), torch.stack(ss).to(DEV)
+    ids = torch.randint(0, E, (8, topk), dtype=torch.int32)
+    ids[:, 1] = (ids[:, 0] + 1) % E
+    tw = torch.rand(8, topk)
+    idsd, twd = ids.to(DEV), tw.to(DEV)
+    none = torch.empty(E, 0, dtype=torch.int32, device=DEV)
+    sorted_ids, _, _ = fm.moe_align_block_size(idsd, 16, E)
+
+    def run():
+        o1 = ops.gptq_marlin_gemm(a_small, mqd, msd, empty, empty, empty, ws, _types().uint4b8, 8, N, K, True, False, True, False)
+        o2 = ops.gptq_marlin_gemm(a_big, mqd, msd, empty, empty, empty, ws, _types().uint4b8, 200, N, K, True, False, True, False)
+        o3 = torch.ops._moe_C.marlin_gemm_moe(a_small, q3, sorted_ids, twd, idsd, s3, none, none, ws, 8, N, K, True, E, topk,
+                                              16, True, True)
+        return o1, o2, o3
+
+    eager = [t.clone() for t in run()]
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        outs = run()
+    for _ in range(2):
+        g.replay()
+    torch.cuda.synchronize()
+    for e, o in zip(eager, outs):
+        assert torch.equal(e, o)
+    _check_gemm(outs[0], om.marlin_gemm(a_small.cpu(), w_ref))
+    _check_gemm(outs[2], om.marlin_gemm_moe(a_small.cpu(), refs, ids, tw, True, True))
