@@ -44,7 +44,8 @@ static constexpr int MG_TEAMS = 4;       // dequant teams (4 warps each) working
 static constexpr int MG_DQ_WARPS = 4 * MG_TEAMS;
 static constexpr int MG_WARP_TMA = MG_DQ_WARPS;       // highest warp ids = highest issue priority
 static constexpr int MG_WARP_MMA = MG_DQ_WARPS + 1;
-static constexpr int MG_THREADS = (MG_DQ_WARPS + 2) * 32;
+static constexpr int MG_ISSUERS = 2;                  // MMA issuer warps, interleaved over the chunks (see the issuer role)
+static constexpr int MG_THREADS = (MG_DQ_WARPS + 1 + MG_ISSUERS) * 32;
 static constexpr int MG_W_BYTES = MG_NT * 128;        // 16 KB dequantised weight tile
 static constexpr int MG_RING_DEPTH = 2;               // chunks in flight per warp (x 4 teams = 8 chunks ahead)
 static constexpr int MG_SMEM_TOTAL = 226 * 1024;      // opt-in dynamic shared memory available to one CTA
@@ -191,8 +192,9 @@ marlin_w4a16_tc5_kernel(const __grid_constant__ CUtensorMap tmap_a, const Marlin
   // is then never two phases ahead of the barrier it tests, whatever the team / stage counts (a parity test
   // two phases ahead passes vacuously — the bug class of the attention ring)
   uint64_t* empty = full_w + MG_MAX_STAGES;         // [2][NS]  tcgen05.commit
-  uint64_t* accum_full = empty + 2 * MG_MAX_STAGES; // [1]
+  uint64_t* accum_full = empty + 2 * MG_MAX_STAGES; // [1]  one commit per issuer
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 1);
+  uint32_t* turn = tmem_slot + 1;                   // next chunk whose MMAs may be issued (orders the two issuers)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_base = blockIdx.x * MG_NT;
@@ -231,7 +233,8 @@ marlin_w4a16_tc5_kernel(const __grid_constant__ CUtensorMap tmap_a, const Marlin
       mbar_init(&empty[i], 1);
       mbar_init(&empty[MG_MAX_STAGES + i], 1);
     }
-    mbar_init(accum_full, 1);
+    mbar_init(accum_full, MG_ISSUERS);
+    *turn = 0;
     fence_mbar_init();
   }
   if (warp == MG_WARP_TMA) tmem_alloc(tmem_slot, tmem_cols);
@@ -261,35 +264,55 @@ marlin_w4a16_tc5_kernel(const __grid_constant__ CUtensorMap tmap_a, const Marlin
       }
       if (prof) { g_mg_prof[0] = (unsigned long long)(clock64() - t_role0); g_mg_prof[1] = w0; g_mg_prof[2] = (unsigned long long)nchunks; }
     }
-  } else if (nchunks > 0 && warp == MG_WARP_MMA) {
-    // ===================== MMA issuer =====================
+  } else if (nchunks > 0 && warp >= MG_WARP_MMA) {
+    // ===================== MMA issuers =====================
+    // TWO issuer threads (one per warp), issuer q taking chunks q, q + 2, ...: the per-stage serial chain of one
+    // issuer (mbarrier wait -> descriptors -> 4 UTCHMMA -> commit, ~500 cycles whatever N) was the limiter up to
+    // 128 tokens and above the 512-cycle tensor floor at 256; two chains overlap. All MMAs accumulate into the same
+    // TMEM tile and the tensor pipe executes them in issue order, so the ISSUE order is kept equal to the chunk
+    // order with a shared-memory turn counter (a spin of a few tens of cycles): the accumulator-initialising MMA is
+    // first, and fp32 accumulation order — hence the result — is identical from run to run; only the waits,
+    // descriptor set-up and commits of the two issuers overlap. tcgen05.commit tracks the MMAs of the executing
+    // thread, so each stage is released by the issuer that consumed it, and `accum_full` collects one commit per issuer.
+    const int iq = warp - MG_WARP_MMA;
     if (elect_one()) {
       // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A/B = T, both K-major, N, M = 128
       const uint32_t fmt = std::is_same<T, __nv_bfloat16>::value ? 1u : 0u;   // 0 = F16, 1 = BF16
       const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n_mma >> 3) << 17) |
                              ((uint32_t)(MG_NT >> 4) << 24);
       const bool skip_mma = (p.debug & 2) != 0;
-      int s = 0;
-      uint32_t use = 0;
-      for (int c = 0; c < nchunks; ++c, s = (s + 1 == NS) ? 0 : s + 1, use += (s == 0)) {
+      const bool profq = prof && iq == 0;
+      int s = iq % NS;
+      uint32_t use = (uint32_t)(iq / NS);
+      const uint32_t turn_addr = smem_u32(turn);
+      for (int c = iq; c < nchunks; c += MG_ISSUERS) {
         const uint32_t par = use & 1u;
-        mbar_wait_t(&full_w[s], par, prof, w1);
+        mbar_wait_t(&full_w[s], par, profq, w1);
         tc_fence_after();
-        const long long tm0 = prof ? clock64() : 0;
+        const long long tm0 = profq ? clock64() : 0;
         const uint64_t a_desc = make_sw128_desc(smem_u32(w_s + (size_t)s * MG_W_BYTES));
         const uint64_t b_desc = make_sw128_desc(smem_u32(act_s + (size_t)s * p.act_bytes));
+        {                                           // my turn: every earlier chunk's MMAs have been issued
+          uint32_t t;
+          do {
+            asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(t) : "r"(turn_addr) : "memory");
+          } while (t != (uint32_t)c);
+        }
 #pragma unroll
         for (int ks = 0; ks < MG_KC / 16; ++ks) {
           if (skip_mma) break;
           // advancing 16 k = 32 bytes inside the 128-byte swizzle row = +2 in the descriptor's (addr >> 4) field
           umma_f16(tmem_d, a_desc + (uint64_t)(2 * ks), b_desc + (uint64_t)(2 * ks), idesc, (c > 0 || ks > 0) ? 1u : 0u);
         }
-        const long long tm1 = prof ? clock64() : 0;
+        asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(turn_addr), "r"((uint32_t)c + 1u) : "memory");
+        const long long tm1 = profq ? clock64() : 0;
         umma_commit(&empty[(use & 1u) * MG_MAX_STAGES + s]);   // frees act/w stage s when these MMAs retire
-        if (prof) { w2 += (unsigned long long)(tm1 - tm0); w3 += (unsigned long long)(clock64() - tm1); }
+        if (profq) { w2 += (unsigned long long)(tm1 - tm0); w3 += (unsigned long long)(clock64() - tm1); }
+        s += MG_ISSUERS;
+        while (s >= NS) { s -= NS; ++use; }
       }
-      umma_commit(accum_full);                   // accumulator complete
-      if (prof) { g_mg_prof[4] = (unsigned long long)(clock64() - t_role0); g_mg_prof[5] = w0; g_mg_prof[6] = w1; g_mg_prof[7] = w2; g_mg_prof[16] = w3; }
+      umma_commit(accum_full);                   // this issuer's share of the accumulator is complete
+      if (profq) { g_mg_prof[4] = (unsigned long long)(clock64() - t_role0); g_mg_prof[5] = w0; g_mg_prof[6] = w1; g_mg_prof[7] = w2; g_mg_prof[16] = w3; }
     }
   } else if (nchunks > 0 && warp < MG_DQ_WARPS) {
     // ===================== dequant warps =====================
@@ -679,13 +702,19 @@ static EncodeTiledFn get_encode() {
 static int plan_split_k(int M, int N, int K, int group_size) {
   const int tiles = ((N + MG_NT - 1) / MG_NT) * ((M + MG_TOK - 1) / MG_TOK);
   const int chunks = K / MG_KC;
-  int split = 1;
   const int sms = num_sms();
   if ((M + MG_TOK - 1) / MG_TOK > 32) return 1;   // lock workspace (N/64*16 ints) covers <= 32 token blocks
-  while (tiles * split * 2 <= sms && chunks / (split * 2) >= 8) split *= 2;
-  // keep every split on a group boundary
+  // as many k-splits as keep every split of every tile co-resident (the reduce spins on the tile's lock) with at
+  // least 8 chunks each: 48 tiles -> 3 splits = 144 CTAs (a power-of-two rule left a third of the SMs idle)
+  int split = std::min(sms / std::max(tiles, 1), chunks / 8);
+  if (split < 1) split = 1;
+  // keep every split on a group boundary and none empty
   const int gchunks = group_size > MG_KC ? group_size / MG_KC : 1;
-  while (split > 1 && ((chunks + split - 1) / split) % gchunks != 0) split /= 2;
+  for (; split > 1; --split) {
+    int per = (chunks + split - 1) / split;
+    per = (per + gchunks - 1) / gchunks * gchunks;
+    if ((split - 1) * per < chunks) break;
+  }
   return split;
 }
 
@@ -858,7 +887,17 @@ extern "C" int b200_gptq_marlin_gemm(const void* a, const void* b_q_weight, cons
   p.act_bytes = (box_rows * 128 + 1023) & ~1023;
   fill_group_params(p, size_k, gs);
   const int chunks = size_k / MG_KC;
-  p.chunks_per_split = (chunks + split_k - 1) / split_k;
+  {
+    const int gchunks = gs > MG_KC ? gs / MG_KC : 1;
+    int per = (chunks + split_k - 1) / split_k;
+    per = (per + gchunks - 1) / gchunks * gchunks;            // splits start on group boundaries
+    while (split_k > 1 && (split_k - 1) * per >= chunks) {    // never an empty split
+      --split_k;
+      per = ((chunks + split_k - 1) / split_k + gchunks - 1) / gchunks * gchunks;
+    }
+    p.split_k = split_k;
+    p.chunks_per_split = per;
+  }
   dim3 grid((size_n + MG_NT - 1) / MG_NT, (size_m + MG_TOK - 1) / MG_TOK, split_k);
   return dispatch_marlin<false>(tmap, p, grid, dtype, has_zp, num_bits, (cudaStream_t)stream);
 }
