@@ -32,12 +32,13 @@ def main():
     ap.add_argument("--m", type=int, nargs="+", default=[256])
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--group", type=int, default=128)
+    ap.add_argument("--kn", type=int, nargs=2, action="append", help="K N pair(s) instead of the four Llama-3-8B shapes")
     ap.add_argument("--sustained", action="store_true",
                     help="also time 200 back-to-back launches rotating over weight copies larger than L2 (boosted clocks, no idle gaps)")
     a = ap.parse_args()
     dev = "cuda:0"
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    shapes = [(4096, 6144), (4096, 4096), (4096, 28672), (14336, 4096)]
+    shapes = [tuple(kn) for kn in a.kn] if a.kn else [(4096, 6144), (4096, 4096), (4096, 28672), (14336, 4096)]
     for M in a.m:
         for K, N in shapes:
             x = torch.randn(M, K, device=dev, dtype=torch.bfloat16)
