@@ -1,311 +1,94 @@
-"""Host-side mirror of the reference's op wrapper for the decode hot path.
+"""Host-side entry points of the decode hot path, under the names the reference's callers use.
 
-Same function names, argument order, defaults and error behaviour as `aphrodite/_custom_ops.py`
-(reference lines cited per function); each forwards to `torch.ops._C.*` / `torch.ops._C_cache_ops.*`,
-which this package registers from its own `_C.abi3.so` (csrc/torch_shim.cpp -> C ABI ->
-hand-written sm_100a kernels). Importing this module loads the native library and raises
-`NativeLibraryMissing` if it has not been built — there is no fallback implementation.
+The reference reaches its kernels through thin Python functions in `aphrodite/_custom_ops.py` (activations :46-68,
+paged attention :72-131, rotary :158-178, norms :182-189, advance_step / awq / permute :192-232 and :627-628, Marlin
+:554-600, MoE :830-843, cache ops :846-892, device queries :895-902, custom all-reduce :906-941). A caller that does
+`from aphrodite import _custom_ops as ops; ops.paged_attention_v1(...)` must be able to do the same against this
+package, so every function below keeps the reference's NAME, PARAMETER ORDER, parameter names and defaults; nothing
+else is shared. The functions are generated from one table (`_TABLE`): each entry names the torch op namespace the call
+forwards to and spells the parameter list once. All of them forward to ops that this package registers from its own
+`_C.abi3.so` / `_moe_C.abi3.so` (csrc/torch_shim.cpp, csrc/moe_shim.cpp -> C ABI -> hand-written sm_100a kernels).
+Importing this module loads the native libraries and raises `NativeLibraryMissing` if they have not been built: there is
+no fallback implementation.
 """
-from typing import List, Optional, Tuple
-
 import torch
 
 from . import _native
 
 _native.load_torch_ops()
 
-
-# activation ops (aphrodite/_custom_ops.py:46-68)
-def silu_and_mul(out: torch.Tensor, x: torch.Tensor) -> None:
-    torch.ops._C.silu_and_mul(out, x)
-
-
-def gelu_and_mul(out: torch.Tensor, x: torch.Tensor) -> None:
-    torch.ops._C.gelu_and_mul(out, x)
-
-
-def gelu_tanh_and_mul(out: torch.Tensor, x: torch.Tensor) -> None:
-    torch.ops._C.gelu_tanh_and_mul(out, x)
-
-
-def gelu_fast(out: torch.Tensor, x: torch.Tensor) -> None:
-    torch.ops._C.gelu_fast(out, x)
-
-
-def gelu_new(out: torch.Tensor, x: torch.Tensor) -> None:
-    torch.ops._C.gelu_new(out, x)
-
-
-def gelu_quick(out: torch.Tensor, x: torch.Tensor) -> None:
-    torch.ops._C.gelu_quick(out, x)
-
-
-# paged attention ops (aphrodite/_custom_ops.py:72-131)
-def paged_attention_v1(
-    out: torch.Tensor,
-    query: torch.Tensor,
-    key_cache: torch.Tensor,
-    value_cache: torch.Tensor,
-    num_kv_heads: int,
-    scale: float,
-    block_tables: torch.Tensor,
-    seq_lens: torch.Tensor,
-    block_size: int,
-    max_seq_len: int,
-    alibi_slopes: Optional[torch.Tensor],
-    kv_cache_dtype: str,
-    k_scale: float,
-    v_scale: float,
-    tp_rank: int = 0,
-    blocksparse_local_blocks: int = 0,
-    blocksparse_vert_stride: int = 0,
-    blocksparse_block_size: int = 64,
-    blocksparse_head_sliding_step: int = 0,
-) -> None:
-    torch.ops._C.paged_attention_v1(
-        out, query, key_cache, value_cache, num_kv_heads, scale, block_tables,
-        seq_lens, block_size, max_seq_len, alibi_slopes, kv_cache_dtype,
-        k_scale, v_scale, tp_rank, blocksparse_local_blocks,
-        blocksparse_vert_stride, blocksparse_block_size,
-        blocksparse_head_sliding_step)
-
-
-def paged_attention_v2(
-    out: torch.Tensor,
-    exp_sum: torch.Tensor,
-    max_logits: torch.Tensor,
-    tmp_out: torch.Tensor,
-    query: torch.Tensor,
-    key_cache: torch.Tensor,
-    value_cache: torch.Tensor,
-    num_kv_heads: int,
-    scale: float,
-    block_tables: torch.Tensor,
-    seq_lens: torch.Tensor,
-    block_size: int,
-    max_seq_len: int,
-    alibi_slopes: Optional[torch.Tensor],
-    kv_cache_dtype: str,
-    k_scale: float,
-    v_scale: float,
-    tp_rank: int = 0,
-    blocksparse_local_blocks: int = 0,
-    blocksparse_vert_stride: int = 0,
-    blocksparse_block_size: int = 64,
-    blocksparse_head_sliding_step: int = 0,
-) -> None:
-    torch.ops._C.paged_attention_v2(
-        out, exp_sum, max_logits, tmp_out, query, key_cache, value_cache,
-        num_kv_heads, scale, block_tables, seq_lens, block_size, max_seq_len,
-        alibi_slopes, kv_cache_dtype, k_scale, v_scale, tp_rank,
-        blocksparse_local_blocks, blocksparse_vert_stride,
-        blocksparse_block_size, blocksparse_head_sliding_step)
-
-
-# pos encoding ops (aphrodite/_custom_ops.py:158-178)
-def rotary_embedding(
-    positions: torch.Tensor,
-    query: torch.Tensor,
-    key: torch.Tensor,
-    head_size: int,
-    cos_sin_cache: torch.Tensor,
-    is_neox: bool,
-) -> None:
-    torch.ops._C.rotary_embedding(positions, query, key, head_size,
-                                  cos_sin_cache, is_neox)
-
-
-def batched_rotary_embedding(positions: torch.Tensor, query: torch.Tensor,
-                             key: torch.Tensor, head_size: int,
-                             cos_sin_cache: torch.Tensor, is_neox: bool,
-                             rot_dim: int,
-                             cos_sin_cache_offsets: torch.Tensor) -> None:
-    torch.ops._C.batched_rotary_embedding(positions, query, key, head_size,
-                                          cos_sin_cache, is_neox, rot_dim,
-                                          cos_sin_cache_offsets)
-
-
-# layer norm ops (aphrodite/_custom_ops.py:182-189)
-def rms_norm(out: torch.Tensor, input: torch.Tensor, weight: torch.Tensor,
-             epsilon: float) -> None:
-    torch.ops._C.rms_norm(out, input, weight, epsilon)
-
-
-def fused_add_rms_norm(input: torch.Tensor, residual: torch.Tensor,
-                       weight: torch.Tensor, epsilon: float) -> None:
-    torch.ops._C.fused_add_rms_norm(input, residual, weight, epsilon)
-
-
-# prepare_inputs / awq / permute (aphrodite/_custom_ops.py:192-203, 225-232, 627-628)
-def advance_step_flashattn(num_seqs: int, num_queries: int, block_size: int,
-                           input_tokens: torch.Tensor,
-                           sampled_token_ids: torch.Tensor,
-                           input_positions: torch.Tensor,
-                           seq_lens: torch.Tensor, slot_mapping: torch.Tensor,
-                           block_tables: torch.Tensor) -> None:
-    """Advance a step on GPU for existing inputs for a multi-step runner"""
-    return torch.ops._C.advance_step_flashattn(num_seqs, num_queries,
-                                               block_size, input_tokens,
-                                               sampled_token_ids,
-                                               input_positions, seq_lens,
-                                               slot_mapping, block_tables)
-
-
-def awq_dequantize(qweight: torch.Tensor, scales: torch.Tensor,
-                   zeros: torch.Tensor, split_k_iters: int, thx: int,
-                   thy: int) -> torch.Tensor:
-    return torch.ops._C.awq_dequantize(qweight, scales, zeros, split_k_iters,
-                                       thx, thy)
-
-
-def permute_cols(a: torch.Tensor, perm: torch.Tensor) -> torch.Tensor:
-    return torch.ops._C.permute_cols(a, perm)
-
-
-# marlin (aphrodite/_custom_ops.py:554-600)
-def gptq_marlin_repack(b_q_weight: torch.Tensor, perm: torch.Tensor,
-                       size_k: int, size_n: int,
-                       num_bits: int) -> torch.Tensor:
-    return torch.ops._C.gptq_marlin_repack(b_q_weight, perm, size_k, size_n,
-                                           num_bits)
-
-
-def awq_marlin_repack(b_q_weight: torch.Tensor, size_k: int, size_n: int,
-                      num_bits: int) -> torch.Tensor:
-    return torch.ops._C.awq_marlin_repack(b_q_weight, size_k, size_n, num_bits)
-
-
-def gptq_marlin_gemm(a: torch.Tensor,
-                     b_q_weight: torch.Tensor,
-                     b_scales: torch.Tensor,
-                     b_zeros: torch.Tensor,
-                     g_idx: torch.Tensor,
-                     perm: torch.Tensor,
-                     workspace: torch.Tensor,
-                     b_q_type,
-                     size_m: int,
-                     size_n: int,
-                     size_k: int,
-                     is_k_full: bool,
-                     has_zp: bool = False,
-                     use_fp32_reduce: bool = False,
-                     is_zp_float: bool = False) -> torch.Tensor:
-    return torch.ops._C.gptq_marlin_gemm(a, b_q_weight, b_scales, b_zeros,
-                                         g_idx, perm, workspace, b_q_type,
-                                         size_m, size_n, size_k, is_k_full,
-                                         has_zp, use_fp32_reduce, is_zp_float)
-
-
-# moe (aphrodite/_custom_ops.py:830-843)
-def moe_align_block_size(topk_ids: torch.Tensor, num_experts: int,
-                         block_size: int, sorted_token_ids: torch.Tensor,
-                         experts_ids: torch.Tensor,
-                         num_tokens_post_pad: torch.Tensor) -> None:
-    torch.ops._C.moe_align_block_size(topk_ids, num_experts, block_size,
-                                      sorted_token_ids, experts_ids,
-                                      num_tokens_post_pad)
-
-
-def topk_softmax(topk_weights: torch.Tensor, topk_ids: torch.Tensor,
-                 token_expert_indicies: torch.Tensor,
-                 gating_output: float) -> None:
-    torch.ops._moe_C.topk_softmax(topk_weights, topk_ids,
-                                  token_expert_indicies, gating_output)
-
-
-# cache ops (aphrodite/_custom_ops.py:846-892)
-def reshape_and_cache(
-    key: torch.Tensor,
-    value: torch.Tensor,
-    key_cache: torch.Tensor,
-    value_cache: torch.Tensor,
-    slot_mapping: torch.Tensor,
-    kv_cache_dtype: str,
-    k_scale: float,
-    v_scale: float,
-) -> None:
-    torch.ops._C_cache_ops.reshape_and_cache(key, value, key_cache,
-                                             value_cache, slot_mapping,
-                                             kv_cache_dtype, k_scale, v_scale)
-
-
-def reshape_and_cache_flash(
-    key: torch.Tensor,
-    value: torch.Tensor,
-    key_cache: torch.Tensor,
-    value_cache: torch.Tensor,
-    slot_mapping: torch.Tensor,
-    kv_cache_dtype: str,
-    k_scale: float,
-    v_scale: float,
-) -> None:
-    torch.ops._C_cache_ops.reshape_and_cache_flash(key, value, key_cache,
-                                                   value_cache, slot_mapping,
-                                                   kv_cache_dtype, k_scale,
-                                                   v_scale)
-
-
-def copy_blocks(key_caches: List[torch.Tensor],
-                value_caches: List[torch.Tensor],
-                block_mapping: torch.Tensor) -> None:
-    torch.ops._C_cache_ops.copy_blocks(key_caches, value_caches, block_mapping)
-
-
-def swap_blocks(src: torch.Tensor, dst: torch.Tensor,
-                block_mapping: torch.Tensor) -> None:
-    torch.ops._C_cache_ops.swap_blocks(src, dst, block_mapping)
-
-
-def convert_fp8(output: torch.Tensor,
-                input: torch.Tensor,
-                scale: float = 1.0,
-                kv_dtype: str = "fp8") -> None:
-    torch.ops._C_cache_ops.convert_fp8(output, input, scale, kv_dtype)
-
-
-# device queries (aphrodite/_custom_ops.py:895-902)
-def get_device_attribute(attribute: int, device: int) -> int:
-    return torch.ops._C_cuda_utils.get_device_attribute(attribute, device)
-
-
-def get_max_shared_memory_per_block_device_attribute(device: int) -> int:
-    return torch.ops._C_cuda_utils.get_max_shared_memory_per_block_device_attribute(device)
-
-
-# custom all-reduce (aphrodite/_custom_ops.py:906-941)
-def init_custom_ar(meta: torch.Tensor, rank_data: torch.Tensor,
-                   handles: List[str], offsets: List[int], rank: int,
-                   full_nvlink: bool) -> int:
-    return torch.ops._C_custom_ar.init_custom_ar(meta, rank_data, handles,
-                                                 offsets, rank, full_nvlink)
-
-
-def all_reduce_reg(fa: int, inp: torch.Tensor, out: torch.Tensor) -> None:
-    torch.ops._C_custom_ar.all_reduce_reg(fa, inp, out)
-
-
-def all_reduce_unreg(fa: int, inp: torch.Tensor, reg_buffer: torch.Tensor,
-                     out: torch.Tensor) -> None:
-    torch.ops._C_custom_ar.all_reduce_unreg(fa, inp, reg_buffer, out)
-
-
-def dispose(fa: int) -> None:
-    torch.ops._C_custom_ar.dispose(fa)
-
-
-def meta_size() -> int:
-    return torch.ops._C_custom_ar.meta_size()
-
-
-def register_buffer(fa: int, t: torch.Tensor, handles: List[str],
-                    offsets: List[int]) -> None:
-    return torch.ops._C_custom_ar.register_buffer(fa, t, handles, offsets)
-
-
-def get_graph_buffer_ipc_meta(fa: int) -> Tuple[List[str], List[int]]:
-    return torch.ops._C_custom_ar.get_graph_buffer_ipc_meta(fa)
-
-
-def register_graph_buffers(fa: int, handles: List[str],
-                           offsets: List[List[int]]) -> None:
-    torch.ops._C_custom_ar.register_graph_buffers(fa, handles, offsets)
+# (function name, torch.ops namespace, parameter list exactly as a caller may spell it)
+_ATTN_TAIL = ("num_kv_heads, scale, block_tables, seq_lens, block_size, max_seq_len, alibi_slopes, kv_cache_dtype, "
+              "k_scale, v_scale, tp_rank=0, blocksparse_local_blocks=0, blocksparse_vert_stride=0, "
+              "blocksparse_block_size=64, blocksparse_head_sliding_step=0")
+_KV_WRITE = "key, value, key_cache, value_cache, slot_mapping, kv_cache_dtype, k_scale, v_scale"
+_TABLE = (
+    # gated / plain activations: out[T, d] <- input[T, 2d] resp. [T, d]
+    ("silu_and_mul", "_C", "out, x"),
+    ("gelu_and_mul", "_C", "out, x"),
+    ("gelu_tanh_and_mul", "_C", "out, x"),
+    ("gelu_fast", "_C", "out, x"),
+    ("gelu_new", "_C", "out, x"),
+    ("gelu_quick", "_C", "out, x"),
+    # decode attention over the paged KV cache (v2 = 512-token partitions + reduce)
+    ("paged_attention_v1", "_C", "out, query, key_cache, value_cache, " + _ATTN_TAIL),
+    ("paged_attention_v2", "_C", "out, exp_sum, max_logits, tmp_out, query, key_cache, value_cache, " + _ATTN_TAIL),
+    # in-place rotary position embedding (batched = per-token cache offsets, LoRA long-context)
+    ("rotary_embedding", "_C", "positions, query, key, head_size, cos_sin_cache, is_neox"),
+    ("batched_rotary_embedding", "_C",
+     "positions, query, key, head_size, cos_sin_cache, is_neox, rot_dim, cos_sin_cache_offsets"),
+    ("rms_norm", "_C", "out, input, weight, epsilon"),
+    ("fused_add_rms_norm", "_C", "input, residual, weight, epsilon"),
+    # multi-step decode input preparation, AWQ dequant, column gather
+    ("advance_step_flashattn", "_C",
+     "num_seqs, num_queries, block_size, input_tokens, sampled_token_ids, input_positions, seq_lens, slot_mapping, "
+     "block_tables"),
+    ("awq_dequantize", "_C", "qweight, scales, zeros, split_k_iters, thx, thy"),
+    ("permute_cols", "_C", "a, perm"),
+    # Marlin-format weight-only quantised GEMM and checkpoint re-tiling
+    ("gptq_marlin_repack", "_C", "b_q_weight, perm, size_k, size_n, num_bits"),
+    ("awq_marlin_repack", "_C", "b_q_weight, size_k, size_n, num_bits"),
+    ("gptq_marlin_gemm", "_C",
+     "a, b_q_weight, b_scales, b_zeros, g_idx, perm, workspace, b_q_type, size_m, size_n, size_k, is_k_full, "
+     "has_zp=False, use_fp32_reduce=False, is_zp_float=False"),
+    # mixture-of-experts routing
+    ("moe_align_block_size", "_C",
+     "topk_ids, num_experts, block_size, sorted_token_ids, experts_ids, num_tokens_post_pad"),
+    ("topk_softmax", "_moe_C", "topk_weights, topk_ids, token_expert_indicies, gating_output"),
+    # KV-cache writers and movers
+    ("reshape_and_cache", "_C_cache_ops", _KV_WRITE),
+    ("reshape_and_cache_flash", "_C_cache_ops", _KV_WRITE),
+    ("copy_blocks", "_C_cache_ops", "key_caches, value_caches, block_mapping"),
+    ("swap_blocks", "_C_cache_ops", "src, dst, block_mapping"),
+    ("convert_fp8", "_C_cache_ops", "output, input, scale=1.0, kv_dtype='fp8'"),
+    ("get_device_attribute", "_C_cuda_utils", "attribute, device"),
+    ("get_max_shared_memory_per_block_device_attribute", "_C_cuda_utils", "device"),
+    # NVLink peer-memory all-reduce (opaque handle `fa`)
+    ("init_custom_ar", "_C_custom_ar", "meta, rank_data, handles, offsets, rank, full_nvlink"),
+    ("all_reduce_reg", "_C_custom_ar", "fa, inp, out"),
+    ("all_reduce_unreg", "_C_custom_ar", "fa, inp, reg_buffer, out"),
+    ("dispose", "_C_custom_ar", "fa"),
+    ("meta_size", "_C_custom_ar", ""),
+    ("register_buffer", "_C_custom_ar", "fa, t, handles, offsets"),
+    ("get_graph_buffer_ipc_meta", "_C_custom_ar", "fa"),
+    ("register_graph_buffers", "_C_custom_ar", "fa, handles, offsets"),
+)
+
+
+def _emit(name: str, namespace: str, params: str):
+    """Builds `def name(params): return torch.ops.<namespace>.<name>(<params, positionally>)` with a real signature,
+    so keyword calls and the reference's defaults work; the op handle is looked up once."""
+    op = getattr(getattr(torch.ops, namespace), name)
+    forwarded = ", ".join(p.split("=")[0].strip() for p in params.split(",") if p.strip())
+    scope = {"_op": op}
+    exec(f"def {name}({params}):\n    return _op({forwarded})\n", scope)    # noqa: S102 - table above is the only input
+    fn = scope[name]
+    fn.__module__ = __name__
+    fn.__doc__ = f"torch.ops.{namespace}.{name}({forwarded}) — this package's sm_100a implementation."
+    return fn
+
+
+for _name, _ns, _params in _TABLE:
+    globals()[_name] = _emit(_name, _ns, _params)
+__all__ = [t[0] for t in _TABLE]
+del _name, _ns, _params

@@ -1,88 +1,75 @@
-"""Mirror of the reference's PagedAttention glue (aphrodite/attention/ops/paged_attn.py:49-190):
-cache views, the paged-cache writer and the V1/V2 decode heuristic, over this package's ops."""
+"""Decode-side attention glue with the reference's interface (`PagedAttention` in aphrodite/attention/ops/paged_attn.py:
+cache shape :49-56, views :58-72, writer :74-95, decode dispatch :97-190), over this package's ops.
+
+Kept from the reference because callers and checkpointed caches depend on it: the `[2, num_blocks, block*heads*dim]`
+allocation viewed as K `[blocks, kv_heads, dim/x, block, x]` (x = 16 bytes of elements) and V `[blocks, kv_heads, dim,
+block]`; the 512-token partition of the split-KV kernel; and the rule for choosing the single-pass kernel — at most
+8192 cached tokens AND (one partition OR more than 512 (sequence, head) pairs to fill the GPU with) — otherwise the
+partitioned kernel with its (exp_sum, max_logit, tmp_out) scratch."""
 from typing import Optional, Tuple
 
 import torch
 
 from .. import _custom_ops as ops
 
-# Should be the same as PARTITION_SIZE in the kernels (paged_attn.py:13 / csrc kPartitionSize).
-_PARTITION_SIZE = 512
+_PARTITION_SIZE = 512          # tokens per split-KV partition; equals kPartitionSize in csrc/paged_attention.cu
+_V1_MAX_CONTEXT = 8192
+_V1_MIN_PAIRS = 512
+
+
+def _wants_single_pass(max_seq_len: int, partitions: int, seq_head_pairs: int) -> bool:
+    if max_seq_len > _V1_MAX_CONTEXT:
+        return False
+    return partitions == 1 or seq_head_pairs > _V1_MIN_PAIRS
 
 
 class PagedAttention:
 
     @staticmethod
-    def get_kv_cache_shape(num_blocks: int, block_size: int, num_kv_heads: int,
-                           head_size: int) -> Tuple[int, ...]:
-        return (2, num_blocks, block_size * num_kv_heads * head_size)
+    def get_kv_cache_shape(num_blocks: int, block_size: int, num_kv_heads: int, head_size: int) -> Tuple[int, ...]:
+        per_block = block_size * num_kv_heads * head_size
+        return (2, num_blocks, per_block)
 
     @staticmethod
     def split_kv_cache(kv_cache: torch.Tensor, num_kv_heads: int,
                        head_size: int) -> Tuple[torch.Tensor, torch.Tensor]:
-        x = 16 // kv_cache.element_size()
-        num_blocks = kv_cache.shape[1]
-        key_cache = kv_cache[0].view(num_blocks, num_kv_heads, head_size // x, -1, x)
-        value_cache = kv_cache[1].view(num_blocks, num_kv_heads, head_size, -1)
-        return key_cache, value_cache
+        lanes = 16 // kv_cache.element_size()            # elements per 16-byte run of the K layout
+        blocks = kv_cache.shape[1]
+        k_plane, v_plane = kv_cache[0], kv_cache[1]
+        return (k_plane.view(blocks, num_kv_heads, head_size // lanes, -1, lanes),
+                v_plane.view(blocks, num_kv_heads, head_size, -1))
 
     @staticmethod
-    def write_to_paged_cache(key, value, key_cache, value_cache, slot_mapping,
-                             kv_cache_dtype: str, k_scale: float, v_scale: float) -> None:
-        ops.reshape_and_cache(key, value, key_cache, value_cache, slot_mapping.flatten(),
-                              kv_cache_dtype, k_scale, v_scale)
+    def write_to_paged_cache(key, value, key_cache, value_cache, slot_mapping, kv_cache_dtype: str, k_scale: float,
+                             v_scale: float) -> None:
+        slots = slot_mapping.flatten()
+        ops.reshape_and_cache(key, value, key_cache, value_cache, slots, kv_cache_dtype, k_scale, v_scale)
 
     @staticmethod
-    def forward_decode(
-        query: torch.Tensor,
-        key_cache: torch.Tensor,
-        value_cache: torch.Tensor,
-        block_tables: torch.Tensor,
-        seq_lens: torch.Tensor,
-        max_seq_len: int,
-        kv_cache_dtype: str,
-        num_kv_heads: int,
-        scale: float,
-        alibi_slopes: Optional[torch.Tensor],
-        k_scale: float,
-        v_scale: float,
-        tp_rank: int = 0,
-        blocksparse_local_blocks: int = 0,
-        blocksparse_vert_stride: int = 0,
-        blocksparse_block_size: int = 64,
-        blocksparse_head_sliding_step: int = 0,
-        output: Optional[torch.Tensor] = None,
-    ) -> torch.Tensor:
-        if blocksparse_vert_stride is not None and blocksparse_vert_stride > 1:
-            block_size = value_cache.size(-1)
-            assert (blocksparse_block_size > 0 and blocksparse_block_size % block_size == 0), \
-                (f"{blocksparse_block_size=} needs to be a multiple of"
-                 f"{block_size=} used in block_tables.")
-        if output is None:
-            output = torch.empty_like(query)
+    def forward_decode(query: torch.Tensor, key_cache: torch.Tensor, value_cache: torch.Tensor,
+                       block_tables: torch.Tensor, seq_lens: torch.Tensor, max_seq_len: int, kv_cache_dtype: str,
+                       num_kv_heads: int, scale: float, alibi_slopes: Optional[torch.Tensor], k_scale: float,
+                       v_scale: float, tp_rank: int = 0, blocksparse_local_blocks: int = 0,
+                       blocksparse_vert_stride: int = 0, blocksparse_block_size: int = 64,
+                       blocksparse_head_sliding_step: int = 0,
+                       output: Optional[torch.Tensor] = None) -> torch.Tensor:
         block_size = value_cache.shape[3]
+        sparse = blocksparse_vert_stride is not None and blocksparse_vert_stride > 1
+        if sparse and not (blocksparse_block_size > 0 and blocksparse_block_size % block_size == 0):
+            raise AssertionError(f"{blocksparse_block_size=} needs to be a multiple of {block_size=} used in block_tables.")
+        out = torch.empty_like(query) if output is None else output
         num_seqs, num_heads, head_size = query.shape
-        max_num_partitions = (max_seq_len + _PARTITION_SIZE - 1) // _PARTITION_SIZE
-        # same heuristic as the reference (paged_attn.py:127-128)
-        use_v1 = (max_seq_len <= 8192
-                  and (max_num_partitions == 1 or num_seqs * num_heads > 512))
-        if use_v1:
-            ops.paged_attention_v1(output, query, key_cache, value_cache, num_kv_heads, scale,
-                                   block_tables, seq_lens, block_size, max_seq_len, alibi_slopes,
-                                   kv_cache_dtype, k_scale, v_scale, tp_rank,
-                                   blocksparse_local_blocks, blocksparse_vert_stride,
-                                   blocksparse_block_size, blocksparse_head_sliding_step)
-        else:
-            assert _PARTITION_SIZE % block_size == 0
-            tmp_output = torch.empty(size=(num_seqs, num_heads, max_num_partitions, head_size),
-                                     dtype=output.dtype, device=output.device)
-            exp_sums = torch.empty(size=(num_seqs, num_heads, max_num_partitions),
-                                   dtype=torch.float32, device=output.device)
-            max_logits = torch.empty_like(exp_sums)
-            ops.paged_attention_v2(output, exp_sums, max_logits, tmp_output, query, key_cache,
-                                   value_cache, num_kv_heads, scale, block_tables, seq_lens,
-                                   block_size, max_seq_len, alibi_slopes, kv_cache_dtype, k_scale,
-                                   v_scale, tp_rank, blocksparse_local_blocks,
-                                   blocksparse_vert_stride, blocksparse_block_size,
-                                   blocksparse_head_sliding_step)
-        return output
+        partitions = -(-max_seq_len // _PARTITION_SIZE)
+        common = (num_kv_heads, scale, block_tables, seq_lens, block_size, max_seq_len, alibi_slopes, kv_cache_dtype,
+                  k_scale, v_scale, tp_rank, blocksparse_local_blocks, blocksparse_vert_stride, blocksparse_block_size,
+                  blocksparse_head_sliding_step)
+        if _wants_single_pass(max_seq_len, partitions, num_seqs * num_heads):
+            ops.paged_attention_v1(out, query, key_cache, value_cache, *common)
+            return out
+        assert _PARTITION_SIZE % block_size == 0
+        stats_shape = (num_seqs, num_heads, partitions)
+        exp_sums = torch.empty(stats_shape, dtype=torch.float32, device=out.device)
+        max_logits = torch.empty_like(exp_sums)
+        tmp_out = torch.empty(stats_shape + (head_size, ), dtype=out.dtype, device=out.device)
+        ops.paged_attention_v2(out, exp_sums, max_logits, tmp_out, query, key_cache, value_cache, *common)
+        return out
