@@ -1,8 +1,12 @@
 """Property tests of the launch-partition arithmetic of the Marlin kernels, restated in Python line by line.
-`small_partition` on the host, the `u / cta_of / nseg / slab index` arithmetic in the kernel), restated in Python
-line by line: for every shape and SM count each (tile, chunk) unit is processed exactly once, every CTA contributes at
-most one segment per tile, slab indices are unique per tile and below the bound `b200_marlin_gemm_plan` reports (the size
-of the caller's fp32 scratch), and the ticket count a tile waits for equals the number of CTAs that touch it."""
+
+Small-batch kernel (csrc/marlin_gemm_small.cu: `small_partition` on the host, the `u / cta_of / nseg / slab index`
+arithmetic in the kernel): for every shape and SM count each (tile, chunk) unit is processed exactly once, every CTA
+contributes at most one segment per tile, slab indices are unique per tile and below the bound `b200_marlin_gemm_plan`
+reports (the size of the caller's fp32 scratch), and the ticket count a tile waits for equals the number of CTAs that touch
+it. tcgen05 kernel (csrc/marlin_gemm.cu): the k-split actually launched never exceeds the planned bound, never leaves
+a split empty and keeps all splits co-resident. Grouped (MoE) launch: the upper-bound grid enumerates every sorted row
+exactly once."""
 import random
 
 import pytest
