@@ -170,3 +170,22 @@ def test_moe_tile_enumeration_covers_every_sorted_row():
             for r in range(base, base + min(tile_rows, offsets[e + 1] - offsets[e] - t * tile_rows)):
                 seen[r] += 1
         assert all(v == 1 for v in seen)
+
+
+def test_python_restatement_equals_the_library_plan():
+    """b200_marlin_gemm_plan runs without a GPU (148 SMs assumed): the restatements above are the shipped arithmetic."""
+    from aphrodite_engine_b200 import _native
+    lib = _native.load_c_abi()
+    rng = random.Random(11)
+    cases = [(256, 6144, 4096, 128), (256, 28672, 4096, 128), (256, 4096, 14336, 128), (16, 28672, 4096, 128),
+             (1, 4096, 4096, -1), (32, 6144, 4096, 128), (33, 6144, 4096, 128), (7, 128256, 4096, 128)]
+    cases += [(rng.randint(1, 600), 64 * rng.randint(1, 500), 64 * rng.randint(1, 256), rng.choice([-1, 32, 64, 128]))
+              for _ in range(200)]
+    for M, N, K, gs in cases:
+        if gs > 0 and K % gs:
+            continue
+        groups = K // gs if gs > 0 else 1
+        expect = _plan_split_k(M, N, K, gs if groups > 1 else -1, 148)
+        if M <= 32:
+            expect = max(expect, small_partition(N, K, 148)[1])
+        assert lib.b200_marlin_gemm_plan(M, N, K, groups) == expect, (M, N, K, gs)
