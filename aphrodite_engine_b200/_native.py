@@ -64,10 +64,14 @@ SIGNATURES = {
     "b200_car_all_reduce": [c_int64, c_void_p, c_void_p, c_int64, c_int, c_void_p],
     "b200_car_get_graph_buffer_ipc_meta": [c_int64, c_void_p, c_void_p, c_int],
     "b200_car_register_graph_buffers": [c_int64, c_void_p, c_void_p, c_int],
+    "b200_tp_flag_bytes": [],
+    "b200_tp_allreduce_rows": [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p,
+                               c_float] + [c_int] * 5 + [c_void_p],
     "b200_get_device_attribute": [c_int64, c_int64],
     "b200_get_max_shared_memory_per_block_device_attribute": [c_int64],
 }
 _RESTYPES = {
+    "b200_tp_flag_bytes": c_int64,
     "b200_car_meta_size": c_int64,
     "b200_car_init": c_int64,
     "b200_car_dispose": None,

@@ -24,6 +24,9 @@ def _wants_single_pass(max_seq_len: int, partitions: int, seq_head_pairs: int) -
 
 
 class PagedAttention:
+    # the op table the two kernel-calling methods use; a subclass may point it at another implementation of the same
+    # op names (bench.py's reference-CUDA arm does, to time the reference's kernels under the identical call pattern)
+    _ops = ops
 
     @staticmethod
     def get_kv_cache_shape(num_blocks: int, block_size: int, num_kv_heads: int, head_size: int) -> Tuple[int, ...]:
@@ -39,14 +42,14 @@ class PagedAttention:
         return (k_plane.view(blocks, num_kv_heads, head_size // lanes, -1, lanes),
                 v_plane.view(blocks, num_kv_heads, head_size, -1))
 
-    @staticmethod
-    def write_to_paged_cache(key, value, key_cache, value_cache, slot_mapping, kv_cache_dtype: str, k_scale: float,
+    @classmethod
+    def write_to_paged_cache(cls, key, value, key_cache, value_cache, slot_mapping, kv_cache_dtype: str, k_scale: float,
                              v_scale: float) -> None:
         slots = slot_mapping.flatten()
-        ops.reshape_and_cache(key, value, key_cache, value_cache, slots, kv_cache_dtype, k_scale, v_scale)
+        cls._ops.reshape_and_cache(key, value, key_cache, value_cache, slots, kv_cache_dtype, k_scale, v_scale)
 
-    @staticmethod
-    def forward_decode(query: torch.Tensor, key_cache: torch.Tensor, value_cache: torch.Tensor,
+    @classmethod
+    def forward_decode(cls, query: torch.Tensor, key_cache: torch.Tensor, value_cache: torch.Tensor,
                        block_tables: torch.Tensor, seq_lens: torch.Tensor, max_seq_len: int, kv_cache_dtype: str,
                        num_kv_heads: int, scale: float, alibi_slopes: Optional[torch.Tensor], k_scale: float,
                        v_scale: float, tp_rank: int = 0, blocksparse_local_blocks: int = 0,
@@ -64,12 +67,12 @@ class PagedAttention:
                   k_scale, v_scale, tp_rank, blocksparse_local_blocks, blocksparse_vert_stride, blocksparse_block_size,
                   blocksparse_head_sliding_step)
         if _wants_single_pass(max_seq_len, partitions, num_seqs * num_heads):
-            ops.paged_attention_v1(out, query, key_cache, value_cache, *common)
+            cls._ops.paged_attention_v1(out, query, key_cache, value_cache, *common)
             return out
         assert _PARTITION_SIZE % block_size == 0
         stats_shape = (num_seqs, num_heads, partitions)
         exp_sums = torch.empty(stats_shape, dtype=torch.float32, device=out.device)
         max_logits = torch.empty_like(exp_sums)
         tmp_out = torch.empty(stats_shape + (head_size, ), dtype=out.dtype, device=out.device)
-        ops.paged_attention_v2(out, exp_sums, max_logits, tmp_out, query, key_cache, value_cache, *common)
+        cls._ops.paged_attention_v2(out, exp_sums, max_logits, tmp_out, query, key_cache, value_cache, *common)
         return out

@@ -23,8 +23,9 @@ CORE = os.path.join(PKG, "_core_C.abi3.so")
 MOE = os.path.join(PKG, "_moe_C.abi3.so")
 
 CU_SOURCES = ["runtime.cu", "paged_attention.cu", "cache_ops.cu", "norm_rope_act.cu", "marlin_repack.cu",
-              "marlin_gemm.cu", "marlin_gemm_small.cu", "moe_ops.cu", "custom_all_reduce.cu", "misc_ops.cu"]
-HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(ROOT, "include", "b200_decode.h")]
+              "marlin_gemm.cu", "marlin_gemm_small.cu", "moe_ops.cu", "custom_all_reduce.cu", "misc_ops.cu", "tp_fused.cu"]
+HEADERS = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + [
+    os.path.join(ROOT, "include", "b200_decode.h")]
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = [

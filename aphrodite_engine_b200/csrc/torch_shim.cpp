@@ -579,6 +579,35 @@ void register_graph_buffers(fptr_t fa, const std::vector<std::string>& handles,
   check(b200_car_register_graph_buffers(fa, blob.data(), flat.data(), (int)n));
 }
 
+// ---- extensions beyond the reference's op set (namespace _C_b200) --------------------------------------------
+// Fused TP exchange (csrc/tp_fused.cu). `block` is this rank's symmetric allocation; x / out are views into it.
+void tp_allreduce_rows(int64_t mc_base, torch::Tensor& block, const std::vector<int64_t>& peer_bases,
+                       torch::Tensor& x, torch::Tensor& out, const c10::optional<torch::Tensor>& residual,
+                       const c10::optional<torch::Tensor>& weight, double epsilon, int64_t flag_off, int64_t rank,
+                       int64_t world) {
+  const at::cuda::OptionalCUDAGuard guard(device_of(block));
+  TORCH_CHECK(x.dim() == 2 && x.is_contiguous() && out.is_contiguous() && x.sizes() == out.sizes() &&
+              x.scalar_type() == out.scalar_type(), "tp_allreduce_rows: x / out must be contiguous [T, H] of one dtype");
+  char* base = static_cast<char*>(block.data_ptr());
+  const int64_t nbytes = block.numel() * block.element_size();
+  const int64_t in_off = static_cast<char*>(x.data_ptr()) - base, out_off = static_cast<char*>(out.data_ptr()) - base;
+  const int64_t bytes = x.numel() * x.element_size();
+  TORCH_CHECK(in_off >= 0 && in_off + bytes <= nbytes && out_off >= 0 && out_off + bytes <= nbytes,
+              "tp_allreduce_rows: x / out must live inside the symmetric block");
+  TORCH_CHECK((int64_t)peer_bases.size() == world, "tp_allreduce_rows: one peer base per rank");
+  TORCH_CHECK(residual.has_value() == weight.has_value(), "tp_allreduce_rows: residual and weight go together");
+  if (residual) {
+    TORCH_CHECK(residual->is_contiguous() && residual->sizes() == x.sizes() && residual->scalar_type() == x.scalar_type() &&
+                weight->is_contiguous() && weight->numel() == x.size(1) && weight->scalar_type() == x.scalar_type(),
+                "tp_allreduce_rows: residual [T, H] / weight [H] of x's dtype");
+  }
+  check(b200_tp_allreduce_rows(reinterpret_cast<void*>(mc_base), base, peer_bases.data(), in_off, out_off, flag_off,
+                               residual ? residual->data_ptr() : nullptr, weight ? weight->data_ptr() : nullptr,
+                               (float)epsilon, (int)x.size(0), (int)x.size(1), (int)rank, (int)world,
+                               dtype_code(x, "tp_allreduce_rows"), cur_stream()));
+}
+int64_t tp_flag_bytes() { return b200_tp_flag_bytes(); }
+
 }  // namespace
 
 TORCH_LIBRARY(_C, ops) {
@@ -738,6 +767,15 @@ TORCH_LIBRARY(_C_custom_ar, custom_ar) {
   custom_ar.impl("register_buffer", torch::kCUDA, &register_buffer);
   custom_ar.def("get_graph_buffer_ipc_meta", &get_graph_buffer_ipc_meta);
   custom_ar.def("register_graph_buffers", &register_graph_buffers);
+}
+
+// This repo's own additions (not part of the reference's op set; see INTEGRATION.md "extensions")
+TORCH_LIBRARY(_C_b200, ext) {
+  ext.def(
+      "tp_allreduce_rows(int mc_base, Tensor block, int[] peer_bases, Tensor x, Tensor! out, "
+      "Tensor!? residual, Tensor? weight, float epsilon, int flag_off, int rank, int world) -> ()");
+  ext.impl("tp_allreduce_rows", torch::kCUDA, &tp_allreduce_rows);
+  ext.def("tp_flag_bytes", &tp_flag_bytes);
 }
 
 // `import <pkg>._C` support (kernels/core/registration.h:22-27 of the reference does the same)

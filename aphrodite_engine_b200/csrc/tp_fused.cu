@@ -1,0 +1,276 @@
+// tp_fused.cu — the tensor-parallel exchange step of a decode layer as ONE kernel over NVSwitch, sm_100a.
+//
+// In the reference a row-parallel linear is followed by three launches: the custom all-reduce kernel
+// (kernels/all_reduce/custom_all_reduce.cuh:183-249, call site aphrodite/distributed/parallel_state.py:353-379), then
+// `fused_add_rms_norm` (kernels/layernorm_kernels.cu:204-286) on the replicated result. Every rank adds the same residual
+// and normalises the same [T, H] rows. Here the exchange and the row work are one kernel and the rows are SHARDED:
+//
+//   start barrier  (every rank's partial sums are in its symmetric buffer)
+//   rank r, for its T/N rows:   s   = multimem.ld_reduce(X)            NVSwitch sums the N partials in flight (fp32
+//                                                                      accumulate, one 16-bit rounding = the reference
+//                                                                      kernel's `downcast(sum fp32)`, .cuh:150-168)
+//                               z   = T(s + residual); residual = z    (layernorm_kernels.cu:231-234 rounding point)
+//                               out = T(T(z * rsqrt(mean z^2 + eps)) * w)
+//                               multimem.st(H, out)                    NVSwitch replicates the row into every rank's H
+//   end barrier    (all rows of H have landed everywhere; nobody still reads X)
+//
+// so the residual stream is touched by ONE rank per row (rank r keeps rows [r*ceil(T/N), ...) of `residual`, the other
+// rows of its buffer are never read), NVLink carries 2 x T*H*2 bytes per GPU per call (the algorithmic minimum of an
+// all-reduce), and the two flag barriers are one `multimem.red` each (a single instruction signals all peers; every rank
+// polls its OWN memory). NORM = false gives the plain two-shot all-reduce (reduce-scatter by ld_reduce + all-gather by
+// multimem.st). MC = false is the same algorithm over unicast peer pointers (N loads / N stores per packet) for boxes
+// without a multicast mapping; it sums in rank order so all ranks see bit-identical results, like the reference.
+//
+// Memory contract (host side: aphrodite_engine_b200/distributed/nvls.py): one symmetric allocation per rank, mapped at
+// `peer_bases[r]` on every rank and (MC) bound to one multicast object mapped at `mc_base`; the kernel is given byte
+// offsets of X, H and the flag area inside it. Flags are monotonically increasing u32 counters (wrap-safe compares), so
+// there is nothing to reset between launches and the kernel is CUDA-graph capturable (no host-side epoch).
+#include "common.cuh"
+
+namespace b200 {
+
+static constexpr int kTpThreads = 512;
+static constexpr int kTpMaxBlocks = 128;   // flag slots per direction
+static constexpr int kTpMaxRanks = 8;
+
+struct TpParams {
+  char* mc_base;                     // multicast VA of the symmetric block (MC only)
+  char* local_base;                  // this rank's unicast VA of the block
+  char* peer_base[kTpMaxRanks];      // unicast VAs of every rank's block (peer_base[rank] == local_base)
+  int64_t in_off, out_off, flag_off; // byte offsets inside the block
+  void* residual;                    // local [T, H]; only this rank's rows are read / written (NORM only)
+  const void* weight;                // [H] (NORM only)
+  float eps;
+  int num_tokens, hidden, rank, world;
+};
+
+// flag area: u32 counter[kTpMaxBlocks] (signalled by every rank, twice per launch) | u32 epoch[kTpMaxBlocks] (local)
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+template <bool MC>
+__device__ __forceinline__ void tp_signal(const TpParams& p, int slot) {
+  const int64_t off = p.flag_off + (int64_t)slot * 4;
+  if (MC) {
+    if (threadIdx.x == 0)
+      asm volatile("multimem.red.release.sys.global.add.u32 [%0], 1;" ::"l"(p.mc_base + off) : "memory");
+  } else {
+    if ((int)threadIdx.x < p.world)
+      asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(p.peer_base[threadIdx.x] + off) : "memory");
+  }
+}
+__device__ __forceinline__ void tp_wait(const TpParams& p, int slot, uint32_t target) {
+  if (threadIdx.x == 0) {
+    const uint32_t* f = reinterpret_cast<const uint32_t*>(p.local_base + p.flag_off) + slot;
+    while ((int32_t)(ld_acquire_sys_u32(f) - target) < 0) {
+    }
+  }
+  __syncthreads();
+}
+
+template <typename T> struct Pk {   // 16 bytes of T
+  static constexpr int N = 16 / sizeof(T);
+  union {
+    uint4 raw;
+    T e[N];
+  };
+};
+
+template <typename T> __device__ __forceinline__ uint4 mc_ld_reduce(const void* mc_addr);
+template <> __device__ __forceinline__ uint4 mc_ld_reduce<__nv_bfloat16>(const void* a) {
+  uint4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(a) : "memory");
+  return v;
+}
+template <> __device__ __forceinline__ uint4 mc_ld_reduce<__half>(const void* a) {
+  uint4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.f16x2 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void mc_st(void* mc_addr, uint4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc_addr), "r"(v.x), "r"(v.y),
+               "r"(v.z), "r"(v.w) : "memory");
+}
+
+// peer data was written by the peer's previous kernel and published by the start barrier: a plain (non-.nc) load that
+// the compiler may not hoist or cache across the barrier
+__device__ __forceinline__ uint4 ld_peer_v4(const void* a) {
+  uint4 v;
+  asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(a) : "memory");
+  return v;
+}
+
+template <typename T, bool MC>
+__device__ __forceinline__ uint4 tp_reduce_packet(const TpParams& p, int64_t byte_off) {
+  if constexpr (MC) {
+    return mc_ld_reduce<T>(p.mc_base + p.in_off + byte_off);
+  } else {
+  float acc[Pk<T>::N];
+#pragma unroll
+  for (int e = 0; e < Pk<T>::N; ++e) acc[e] = 0.f;
+  Pk<T> v[kTpMaxRanks];
+#pragma unroll
+  for (int r = 0; r < kTpMaxRanks; ++r)   // all peer loads in flight before the first add
+    if (r < p.world) v[r].raw = ld_peer_v4(p.peer_base[r] + p.in_off + byte_off);
+#pragma unroll
+  for (int r = 0; r < kTpMaxRanks; ++r)
+    if (r < p.world) {
+#pragma unroll
+      for (int e = 0; e < Pk<T>::N; ++e) acc[e] += to_f32<T>(v[r].e[e]);
+    }
+  Pk<T> o;
+#pragma unroll
+  for (int e = 0; e < Pk<T>::N; ++e) o.e[e] = from_f32<T>(acc[e]);
+  return o.raw;
+  }
+}
+template <bool MC>
+__device__ __forceinline__ void tp_broadcast_packet(const TpParams& p, int64_t byte_off, uint4 v) {
+  if (MC) {
+    mc_st(p.mc_base + p.out_off + byte_off, v);
+  } else {
+#pragma unroll
+    for (int r = 0; r < kTpMaxRanks; ++r)
+      if (r < p.world) {
+        const int dst = (p.rank + r) % p.world;   // stagger the peers
+        *reinterpret_cast<uint4*>(p.peer_base[dst] + p.out_off + byte_off) = v;
+      }
+  }
+}
+
+// grid = min(rows per rank, kTpMaxBlocks) CTAs (identical on every rank); CTA b owns rows b, b+grid, ... of the slice.
+template <typename T, bool MC, bool NORM, int VPT>
+__global__ void __launch_bounds__(kTpThreads, 1) tp_allreduce_rows_kernel(const TpParams p) {
+  __shared__ float red[kTpThreads / 32];
+  constexpr int N = Pk<T>::N;
+  uint32_t* flags = reinterpret_cast<uint32_t*>(p.local_base + p.flag_off);
+  const uint32_t epoch = flags[kTpMaxBlocks + blockIdx.x];           // launches this slot has seen (local counter)
+  const uint32_t t_start = (2u * epoch + 1u) * (uint32_t)p.world;
+  const uint32_t t_end = (2u * epoch + 2u) * (uint32_t)p.world;
+
+  tp_signal<MC>(p, blockIdx.x);
+  tp_wait(p, blockIdx.x, t_start);
+
+  const int rows_per = (p.num_tokens + p.world - 1) / p.world;
+  const int row0 = p.rank * rows_per;
+  const int row1 = min(p.num_tokens, row0 + rows_per);
+  const int nvec = p.hidden / N;
+  const int64_t row_bytes = (int64_t)p.hidden * sizeof(T);
+  for (int row = row0 + blockIdx.x; row < row1; row += gridDim.x) {
+    Pk<T> z[VPT];
+#pragma unroll
+    for (int k = 0; k < VPT; ++k) {
+      const int v = threadIdx.x + k * kTpThreads;
+      if (v < nvec) z[k].raw = tp_reduce_packet<T, MC>(p, row * row_bytes + (int64_t)v * 16);
+    }
+    if (NORM) {
+      float ss = 0.f;
+      T* res = reinterpret_cast<T*>(p.residual) + (int64_t)row * p.hidden;
+#pragma unroll
+      for (int k = 0; k < VPT; ++k) {
+        const int v = threadIdx.x + k * kTpThreads;
+        if (v < nvec) {
+          Pk<T> r;
+          r.raw = *reinterpret_cast<const uint4*>(res + (int64_t)v * N);
+#pragma unroll
+          for (int e = 0; e < N; ++e) {
+            z[k].e[e] = from_f32<T>(__fadd_rn(to_f32<T>(z[k].e[e]), to_f32<T>(r.e[e])));
+            const float f = to_f32<T>(z[k].e[e]);
+            ss = fmaf(f, f, ss);
+          }
+          *reinterpret_cast<uint4*>(res + (int64_t)v * N) = z[k].raw;
+        }
+      }
+      ss = warp_sum(ss);
+      __syncthreads();                       // `red` reuse across rows
+      if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+      __syncthreads();
+      float tot = 0.f;
+#pragma unroll
+      for (int i = 0; i < kTpThreads / 32; ++i) tot += red[i];
+      const float s = rsqrtf(tot / (float)p.hidden + p.eps);
+#pragma unroll
+      for (int k = 0; k < VPT; ++k) {
+        const int v = threadIdx.x + k * kTpThreads;
+        if (v < nvec) {
+          Pk<T> w;
+          w.raw = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.weight) + (int64_t)v * N));
+#pragma unroll
+          for (int e = 0; e < N; ++e)
+            z[k].e[e] = from_f32<T>(__fmul_rn(to_f32<T>(from_f32<T>(__fmul_rn(to_f32<T>(z[k].e[e]), s))),
+                                             to_f32<T>(w.e[e])));
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < VPT; ++k) {
+      const int v = threadIdx.x + k * kTpThreads;
+      if (v < nvec) tp_broadcast_packet<MC>(p, row * row_bytes + (int64_t)v * 16, z[k].raw);
+    }
+  }
+  // every thread's stores are ordered before the release-add of the signalling thread(s)
+  __threadfence_system();
+  __syncthreads();
+  tp_signal<MC>(p, blockIdx.x);
+  tp_wait(p, blockIdx.x, t_end);
+  if (threadIdx.x == 0) flags[kTpMaxBlocks + blockIdx.x] = epoch + 1u;
+}
+
+template <typename T, bool MC, bool NORM>
+static int launch_tp(const TpParams& p, cudaStream_t st) {
+  const int nvec = p.hidden / Pk<T>::N;
+  const int rows_per = (p.num_tokens + p.world - 1) / p.world;
+  const int grid = std::max(1, std::min(rows_per, kTpMaxBlocks));
+  if (nvec <= kTpThreads)
+    tp_allreduce_rows_kernel<T, MC, NORM, 1><<<grid, kTpThreads, 0, st>>>(p);
+  else if (nvec <= 2 * kTpThreads)
+    tp_allreduce_rows_kernel<T, MC, NORM, 2><<<grid, kTpThreads, 0, st>>>(p);
+  else
+    tp_allreduce_rows_kernel<T, MC, NORM, 4><<<grid, kTpThreads, 0, st>>>(p);
+  return check_launch("tp_allreduce_rows_kernel");
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int64_t b200_tp_flag_bytes(void) { return (int64_t)(2 * kTpMaxBlocks * sizeof(uint32_t)); }
+
+extern "C" int b200_tp_allreduce_rows(void* mc_base, void* local_base, const int64_t* peer_bases, int64_t in_off,
+                                      int64_t out_off, int64_t flag_off, void* residual, const void* weight,
+                                      float epsilon, int num_tokens, int hidden, int rank, int world, int dtype,
+                                      void* stream) {
+  B200_CHECK(dtype == B200_F16 || dtype == B200_BF16, "tp_allreduce_rows: float16 / bfloat16 only");
+  B200_CHECK(world >= 2 && world <= kTpMaxRanks && rank >= 0 && rank < world, "tp_allreduce_rows: bad rank / world");
+  B200_CHECK(local_base != nullptr && (mc_base != nullptr || peer_bases != nullptr),
+             "tp_allreduce_rows: needs a multicast mapping or the peer table");
+  B200_CHECK(hidden % 8 == 0 && hidden / 8 <= 4 * kTpThreads, "tp_allreduce_rows: hidden must be a multiple of 8, <= 16384");
+  B200_CHECK(((in_off | out_off) & 15) == 0 && (flag_off & 127) == 0, "tp_allreduce_rows: misaligned offsets");
+  B200_CHECK((residual == nullptr) == (weight == nullptr), "tp_allreduce_rows: residual and weight go together");
+  B200_CHECK(((reinterpret_cast<uintptr_t>(residual) | reinterpret_cast<uintptr_t>(weight)) & 15) == 0,
+             "tp_allreduce_rows: residual / weight must be 16-byte aligned");
+  if (num_tokens == 0) return 0;
+  TpParams p;
+  p.mc_base = static_cast<char*>(mc_base);
+  p.local_base = static_cast<char*>(local_base);
+  for (int r = 0; r < kTpMaxRanks; ++r)
+    p.peer_base[r] = (peer_bases != nullptr && r < world) ? reinterpret_cast<char*>(peer_bases[r]) : nullptr;
+  if (peer_bases != nullptr)
+    B200_CHECK(p.peer_base[rank] == p.local_base, "tp_allreduce_rows: peer_bases[rank] must be the local mapping");
+  p.in_off = in_off; p.out_off = out_off; p.flag_off = flag_off;
+  p.residual = residual; p.weight = weight; p.eps = epsilon;
+  p.num_tokens = num_tokens; p.hidden = hidden; p.rank = rank; p.world = world;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool mc = mc_base != nullptr, norm = residual != nullptr;
+#define B200_TP(T)                                                               \
+  (mc ? (norm ? launch_tp<T, true, true>(p, st) : launch_tp<T, true, false>(p, st)) \
+      : (norm ? launch_tp<T, false, true>(p, st) : launch_tp<T, false, false>(p, st)))
+  return dtype == B200_BF16 ? B200_TP(__nv_bfloat16) : B200_TP(__half);
+#undef B200_TP
+}

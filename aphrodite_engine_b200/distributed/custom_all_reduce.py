@@ -32,6 +32,7 @@ def is_weak_contiguous(inp: torch.Tensor) -> bool:
 
 class CustomAllreduce:
     _SUPPORTED_WORLD_SIZES = list(_WORLD_SIZES)
+    _ops = ops      # op table (a checker may substitute the reference's own kernels behind the same protocol)
 
     def __init__(self, group: ProcessGroup, device: Union[int, str, torch.device], max_size: int = 8192 * 1024,
                  full_nvlink: bool = True) -> None:
@@ -50,12 +51,12 @@ class CustomAllreduce:
             return                                       # no P2P between some pair: leave it to NCCL
         self.max_size = max_size
         self.full_nvlink = full_nvlink
-        self.meta = torch.zeros(ops.meta_size() + max_size, dtype=torch.uint8, device=self.device)
+        self.meta = torch.zeros(self._ops.meta_size() + max_size, dtype=torch.uint8, device=self.device)
         self.buffer = torch.empty(max_size, dtype=torch.uint8, device=self.device)
         self.rank_data = torch.empty(_RANK_DATA_BYTES, dtype=torch.uint8, device=self.device)
         self.disabled = False
         handles, offsets = self._exchange(*self._ipc_of(self.meta))
-        self._ptr = ops.init_custom_ar(self.meta, self.rank_data, handles, offsets, self.rank, self.full_nvlink)
+        self._ptr = self._ops.init_custom_ar(self.meta, self.rank_data, handles, offsets, self.rank, self.full_nvlink)
         self.register_buffer(self.buffer)
 
     # ---- IPC plumbing --------------------------------------------------------------------------------------
@@ -75,12 +76,12 @@ class CustomAllreduce:
 
     def register_buffer(self, inp: torch.Tensor):
         handles, offsets = self._exchange(*self._ipc_of(inp))
-        ops.register_buffer(self._ptr, inp, handles, offsets)
+        self._ops.register_buffer(self._ptr, inp, handles, offsets)
 
     def register_graph_buffers(self):
-        handle_bytes, offset_list = ops.get_graph_buffer_ipc_meta(self._ptr)
+        handle_bytes, offset_list = self._ops.get_graph_buffer_ipc_meta(self._ptr)
         handles, offsets = self._exchange(bytes(handle_bytes.numpy().tobytes()), offset_list)
-        ops.register_graph_buffers(self._ptr, handles, offsets)
+        self._ops.register_graph_buffers(self._ptr, handles, offsets)
 
     @contextmanager
     def capture(self):
@@ -107,12 +108,12 @@ class CustomAllreduce:
 
     def all_reduce_reg(self, inp: torch.Tensor, out: Optional[torch.Tensor] = None):
         out = torch.empty_like(inp) if out is None else out
-        ops.all_reduce_reg(self._ptr, inp, out)
+        self._ops.all_reduce_reg(self._ptr, inp, out)
         return out
 
     def all_reduce_unreg(self, inp: torch.Tensor, out: Optional[torch.Tensor] = None):
         out = torch.empty_like(inp) if out is None else out
-        ops.all_reduce_unreg(self._ptr, inp, self.buffer, out)
+        self._ops.all_reduce_unreg(self._ptr, inp, self.buffer, out)
         return out
 
     def custom_all_reduce(self, input: torch.Tensor) -> Optional[torch.Tensor]:
@@ -126,7 +127,7 @@ class CustomAllreduce:
 
     def close(self):
         if not self.disabled and getattr(self, "_ptr", 0):
-            ops.dispose(self._ptr)
+            self._ops.dispose(self._ptr)
             self._ptr = 0
 
     def __del__(self):

@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""bench.py — decode tok/s of the B200 decode hot path (BASELINE.json metric) and its CPU reference.
+"""bench.py — decode tok/s of the B200 decode hot path (BASELINE.json metric) beside the reference.
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU kernels
@@ -7,22 +7,30 @@
 Workload (config.workload): Llama-3-8B bf16 paged-attention decode, bs=256, ctx=4096, block 16,
 random-init weights, synthetic prompts — BASELINE.json configs[1]. A "step" is one full decode step:
 32 decoder layers + final norm + lm_head + greedy token, 256 tokens. N > 1 = the reference's tensor
-parallel split (heads / column-row), two NCCL all-reduces per layer, strong scaling (the batch is fixed).
+parallel split (heads / column-row), one exchange after each row-parallel GEMM, strong scaling (the batch is fixed).
 
 Legs of the default (CUDA) arm, all in one process per GPU:
-  value     CUDA-graph replay of the step, inputs resident in HBM, CUDA events, max over ranks.
+  value     CUDA-graph replay of the step, inputs resident in HBM, one CUDA-event bracket around the K steps
+            (max over ranks) plus an event between steps, so a stall inside the bracket is visible (per_step_ms).
   e2e       same step through the public API with HOST inputs: pinned host->device copy of the step's
             inputs (token ids, positions, slot mapping, seq lens, block tables), graph replay,
             device->host read of the sampled tokens, every step, inside the timed region.
   roofline  paged_attention_v1 (the dominant kernel) timed with CUDA events around each of its launches
             inside eagerly-run steps; achieved = algorithmic bytes per launch / mean launch time, against
             MEASURED_PEAKS.json's HBM copy bandwidth.
+  tp_parity (N > 1) the exchange kernel in use checked EXACTLY against NCCL all-reduce + fused_add_rms_norm on small
+            integers, and a whole eager step compared with the NCCL-exchange step on the same weights / cache.
+  ref_cuda  the SAME step (same weights, cache, call pattern, CUDA-graph replay) over the reference's own CUDA kernels
+            recompiled for sm_100a (oracle/_ref/_ref_cuda_C.so; its custom all-reduce at N > 1): the
+            "reference CUDA build" side of the north-star target. Checker-side code, like cpu_baseline.
   cpu_baseline (rank 0, N=1 only) the reference's CPU kernels (oracle/_ref; torch.matmul for the GEMMs)
             on a bounded sample: decoder layers at the full shape, extrapolated to the 32-layer step.
+  secondary BASELINE configs[2..4] as bounded extra legs (see secondary_legs()).
 The working set of one step (137 GB KV + 16 GB weights) is far larger than L2, so no explicit L2 flush
 is needed between timed iterations.
 """
 import argparse
+import contextlib
 import json
 import os
 import statistics
@@ -37,6 +45,9 @@ sys.path.insert(0, ROOT)
 
 METRIC = "decode tok/s @ bs=256 seq=4k Llama-3-8B"
 UNIT = "tok/s"
+# Llama-3-8B (the reference arm must not import the product package: the constants are spelled here)
+L3 = dict(hidden=4096, layers=32, heads=32, kv_heads=8, head_size=128, intermediate=14336, vocab=128256,
+          rope_theta=500000.0, max_position=8192, rms_eps=1e-5)
 
 
 def parse():
@@ -51,12 +62,14 @@ def parse():
     ap.add_argument("--layers", type=int, default=32, help="debug only; the metric is quoted on 32")
     ap.add_argument("--kv-cache-dtype", default="auto")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-cuda", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--cpu-sample-layers", type=int, default=2)
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--allreduce", default="auto", choices=["auto", "custom", "nccl"],
-                    help="TP all-reduce: NVLink peer-memory kernel or NCCL; auto = the peer-memory kernel up to 4 "
-                         "ranks (verified bit-exact vs NCCL on 2 and 4 GPUs), NCCL at 8 (same speed there, and the "
-                         "8-rank parity run of this round was inconclusive)")
+    ap.add_argument("--allreduce", default="auto", choices=["auto", "nvls", "nvls-p2p", "p2p", "nccl"],
+                    help="TP exchange: nvls = fused NVSwitch-multicast reduce+norm kernel; nvls-p2p = the same kernel over "
+                         "unicast peer pointers; p2p = IPC peer-memory all-reduce kernel + norm; nccl; auto = the first of "
+                         "these that is available AND passes the in-run exact parity check")
     ap.add_argument("--quant", default=None, choices=[None, "gptq"],
                     help="gptq = BASELINE configs[2] (GPTQ int4 Marlin W4A16 linears); default bf16 = configs[1]")
     return ap.parse_args()
@@ -71,13 +84,16 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe). Started BEFORE the
+    warm-up: nvidia-smi's own start-up (NVML attaches to every GPU of the box) perturbs running kernels for tens of
+    milliseconds, which must not land inside the timed bracket; samples are kept from mark() on."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,timestamp")
 
     def __init__(self, index):
         self.index, self.proc, self.path = index, None, f"/tmp/b200_clocks_{os.getpid()}.csv"
+        self.t_mark = None
 
     def start(self):
         try:
@@ -87,6 +103,14 @@ class ClockSampler:
                                          stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
+
+    def mark(self):
+        """Lines written before this moment belong to the warm-up."""
+        try:
+            self.f.flush()
+            self.n_skip = sum(1 for _ in open(self.path))
+        except Exception:
+            self.n_skip = 0
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
@@ -101,7 +125,9 @@ class ClockSampler:
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         try:
-            for line in open(self.path):
+            for i, line in enumerate(open(self.path)):
+                if i < getattr(self, "n_skip", 0):
+                    continue
                 c = [x.strip() for x in line.split(",")]
                 if len(c) < 9:
                     continue
@@ -125,13 +151,13 @@ def cpu_reference_sample(args, n_layers, iters, warmup):
     """Times `n_layers` decoder layers + final norm + lm_head at the full bs/ctx shape on the CPU with
     the reference's kernels (oracle/_ref/*.so built from /root/reference/kernels/cpu) and torch.matmul
     for the unquantised GEMMs (the reference's CPU backend does the same through F.linear).
-    Returns (tok/s extrapolated to 32 layers, seconds per 32-layer step, kind, cores, description)."""
+    Returns a dict: tok/s extrapolated to 32 layers from the MEDIAN layer time, seconds per step, spread."""
     from oracle import ref_lib, paged_ops as po
-    from aphrodite_engine_b200.llama_decode import LlamaShape
     ref = ref_lib.load()
     kind = "reference" if ref is not None else "port"
-    s = LlamaShape()
-    B, CTX, BS, D, H, KV = args.batch, args.ctx, args.block_size, s.head_size, s.heads, s.kv_heads
+    B, CTX, BS = args.batch, args.ctx, args.block_size
+    D, H, KV, HID, INTER, VOCAB, EPS = (L3["head_size"], L3["heads"], L3["kv_heads"], L3["hidden"], L3["intermediate"],
+                                        L3["vocab"], L3["rms_eps"])
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     dt = torch.bfloat16
@@ -153,24 +179,24 @@ def cpu_reference_sample(args, n_layers, iters, warmup):
             flat[off:off + n] = tile[:n]
         kc = kv[0].view(NB, KV, D // 8, BS, 8)
         vc = kv[1].view(NB, KV, D, BS)
-        layers.append(dict(kc=kc, vc=vc, ln1=torch.ones(s.hidden, dtype=dt), ln2=torch.ones(s.hidden, dtype=dt),
-                           qkv=w((H + 2 * KV) * D, s.hidden), o=w(s.hidden, H * D),
-                           gate_up=w(2 * s.intermediate, s.hidden), down=w(s.hidden, s.intermediate)))
-    norm_w, lm_head = torch.ones(s.hidden, dtype=dt), w(s.vocab, s.hidden)
-    inv = 1.0 / (s.rope_theta ** (torch.arange(0, D, 2, dtype=torch.float32) / D))
-    fr = torch.einsum("i,j->ij", torch.arange(s.max_position, dtype=torch.float32), inv)
+        layers.append(dict(kc=kc, vc=vc, ln1=torch.ones(HID, dtype=dt), ln2=torch.ones(HID, dtype=dt),
+                           qkv=w((H + 2 * KV) * D, HID), o=w(HID, H * D),
+                           gate_up=w(2 * INTER, HID), down=w(HID, INTER)))
+    norm_w, lm_head = torch.ones(HID, dtype=dt), w(VOCAB, HID)
+    inv = 1.0 / (L3["rope_theta"] ** (torch.arange(0, D, 2, dtype=torch.float32) / D))
+    fr = torch.einsum("i,j->ij", torch.arange(L3["max_position"], dtype=torch.float32), inv)
     cos_sin = torch.cat((fr.cos(), fr.sin()), dim=-1).to(dt)
     bt = torch.randperm(NB, generator=g).view(B, nb_per).to(torch.int32)
     sl = torch.full((B,), CTX, dtype=torch.int32)
     pos = torch.full((B,), CTX - 1, dtype=torch.long)
     slot = bt[:, (CTX - 1) // BS].long() * BS + (CTX - 1) % BS
-    hidden0 = (torch.randn(B, s.hidden, generator=g)).to(dt)
+    hidden0 = (torch.randn(B, HID, generator=g)).to(dt)
 
     if ref is not None:
         rops, rcache, _ = ref
 
         def layer_fwd(L, hidden, residual):
-            rops.fused_add_rms_norm(hidden, residual, L["ln1"], s.rms_eps)
+            rops.fused_add_rms_norm(hidden, residual, L["ln1"], EPS)
             qkv = torch.nn.functional.linear(hidden, L["qkv"])
             q, k, v = qkv.split([H * D, KV * D, KV * D], dim=-1)
             q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
@@ -180,70 +206,82 @@ def cpu_reference_sample(args, n_layers, iters, warmup):
             rops.paged_attention_v1(out, q.view(B, H, D), L["kc"], L["vc"], KV, scale, bt, sl, BS, CTX,
                                     None, "auto", 1.0, 1.0, 0, 0, 0, 64, 0)
             hidden = torch.nn.functional.linear(out.view(B, -1), L["o"])
-            rops.fused_add_rms_norm(hidden, residual, L["ln2"], s.rms_eps)
+            rops.fused_add_rms_norm(hidden, residual, L["ln2"], EPS)
             gu = torch.nn.functional.linear(hidden, L["gate_up"])
-            act = torch.empty(B, s.intermediate, dtype=dt)
+            act = torch.empty(B, INTER, dtype=dt)
             rops.silu_and_mul(act, gu)
             return torch.nn.functional.linear(act, L["down"]), residual
 
         def head_fwd(hidden, residual):
-            rops.fused_add_rms_norm(hidden, residual, norm_w, s.rms_eps)
+            rops.fused_add_rms_norm(hidden, residual, norm_w, EPS)
             return torch.nn.functional.linear(hidden, lm_head).argmax(dim=-1)
     else:  # host CPU cannot run the AVX-512 build: time the Python/torch restatement instead
         def layer_fwd(L, hidden, residual):
-            hidden, residual = po.fused_add_rms_norm(hidden, residual, L["ln1"], s.rms_eps)
+            hidden, residual = po.fused_add_rms_norm(hidden, residual, L["ln1"], EPS)
             qkv = torch.nn.functional.linear(hidden, L["qkv"])
             q, k, v = qkv.split([H * D, KV * D, KV * D], dim=-1)
             q, k = po.rotary_embedding(pos, q, k, D, cos_sin, True)
             po.reshape_and_cache(k.reshape(B, KV, D), v.reshape(B, KV, D), L["kc"], L["vc"], slot)
             out = po.paged_attention(q.reshape(B, H, D), L["kc"], L["vc"], bt, sl, scale)
             hidden = torch.nn.functional.linear(out.view(B, -1), L["o"])
-            hidden, residual = po.fused_add_rms_norm(hidden, residual, L["ln2"], s.rms_eps)
+            hidden, residual = po.fused_add_rms_norm(hidden, residual, L["ln2"], EPS)
             act = po.silu_and_mul(torch.nn.functional.linear(hidden, L["gate_up"]))
             return torch.nn.functional.linear(act, L["down"]), residual
 
         def head_fwd(hidden, residual):
-            hidden, _ = po.fused_add_rms_norm(hidden, residual, norm_w, s.rms_eps)
+            hidden, _ = po.fused_add_rms_norm(hidden, residual, norm_w, EPS)
             return torch.nn.functional.linear(hidden, lm_head).argmax(dim=-1)
 
     def one_sample():
         hidden, residual = hidden0.clone(), hidden0.clone()
-        t0 = time.perf_counter()
+        per = []
         for L in layers:
+            t0 = time.perf_counter()
             hidden, residual = layer_fwd(L, hidden, residual)
+            per.append(time.perf_counter() - t0)
         t1 = time.perf_counter()
         head_fwd(hidden, residual)
-        t2 = time.perf_counter()
-        return (t1 - t0) / n_layers, t2 - t1
+        return per, time.perf_counter() - t1
 
     for _ in range(warmup):
         one_sample()
-    per_layer, head = [], []
+    layer_s, head_s = [], []
     for _ in range(iters):
         a, b = one_sample()
-        per_layer.append(a); head.append(b)
-    step_s = statistics.mean(per_layer) * s.layers + statistics.mean(head)
+        layer_s += a
+        head_s.append(b)
+    med, mn, mx = statistics.median(layer_s), min(layer_s), max(layer_s)
+    step_s = med * L3["layers"] + statistics.median(head_s)
+    try:
+        load = os.getloadavg()[0]
+    except OSError:
+        load = None
     desc = (f"{n_layers} decoder layer(s) + final norm + lm_head at bs={B} ctx={CTX} bf16 on the CPU "
             f"({'reference kernels/cpu build' if ref is not None else 'python restatement'}; GEMMs via "
-            f"torch.matmul), {iters} timed pass(es), layer time x32 + head")
-    return B / step_s, step_s, kind, cores, desc
+            f"torch.matmul), {iters} timed pass(es) = {len(layer_s)} layer timings; step = median layer x32 + head")
+    return dict(value=B / step_s, step_s=step_s, kind=kind, cores=cores, sample=desc,
+                layer_ms={"median": med * 1e3, "min": mn * 1e3, "max": mx * 1e3, "n": len(layer_s)},
+                head_ms=statistics.median(head_s) * 1e3, host_loadavg_1m=load)
 
 
 def run_reference_arm(args, rank):
     if rank != 0:
         return
-    iters = max(1, min(args.steps, 5))
+    iters = max(1, min(args.steps, 3))
     warm = max(1, min(args.warmup, 1))
     t0 = time.perf_counter()
-    val, step_s, kind, cores, desc = cpu_reference_sample(args, 1, iters, warm)
+    r = cpu_reference_sample(args, 2, iters, warm)
+    val, step_s = r["value"], r["step_s"]
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
         "steps": iters, "warmup": warm, "ms_per_step": step_s * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"Llama-3-8B bf16 paged-attention decode bs={args.batch} ctx={args.ctx} "
-                               f"block={args.block_size} (BASELINE configs[1]); CPU: bounded sample per step",
-                   "l2": "working set >> L2"},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc},
+                               f"block={args.block_size} (BASELINE configs[1]); CPU: each timed step is a bounded sample "
+                               f"(2 of the 32 layers + head), ms_per_step is the extrapolated full step",
+                   "l2": "working set >> L2", "extrapolated": True},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
+                         "layer_ms": r["layer_ms"], "head_ms": r["head_ms"], "host_loadavg_1m": r["host_loadavg_1m"]},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
     }
@@ -253,56 +291,209 @@ def run_reference_arm(args, rank):
 # ================================================================================================
 # CUDA arm
 # ================================================================================================
+class Env:
+    """Process-wide state of the CUDA arm (one rank)."""
+
+    def __init__(self, args):
+        import torch.distributed as dist
+        self.args, self.dist = args, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        assert self.world == args.gpus or self.world == 1, "launch with torchrun --nproc-per-node == --gpus"
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        self.group = self.cpu_group = None
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+            self.group = dist.group.WORLD
+            self.cpu_group = dist.new_group(backend="gloo")
+        self.stream = torch.cuda.Stream(device=self.dev)
+        self.notes = []
+
+    def log(self, msg):
+        if self.rank == 0:
+            print(f"[bench] {msg}", file=sys.stderr, flush=True)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def all_agree(self, ok: bool) -> bool:
+        if self.world == 1:
+            return ok
+        t = torch.tensor([1 if ok else 0], dtype=torch.int32, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)
+        return bool(t.item())
+
+    def max_over_ranks(self, v: float) -> float:
+        if self.world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+
+def exchange_parity_exact(env, mode, nvls, ca, batch, hidden, dtype):
+    """The exchange kernel in use vs NCCL all-reduce + fused_add_rms_norm, small integers (all partial sums exact in
+    bf16, the reference's trick: tests/distributed/test_custom_all_reduce.py:55-81) => torch.equal."""
+    import aphrodite_engine_b200._custom_ops as ops
+    dist, dev = env.dist, env.dev
+    ok = True
+    for it in range(3):
+        torch.manual_seed(4321 + 97 * it + env.rank)
+        x = torch.randint(-3, 4, (batch, hidden), device=dev).to(dtype)
+        res0 = torch.randint(-3, 4, (batch, hidden), device=dev).to(dtype)
+        w = torch.randint(1, 4, (hidden,), device=dev).to(dtype)
+        dist.broadcast(res0, 0)
+        dist.broadcast(w, 0)
+        ref_h = x.clone()
+        dist.all_reduce(ref_h)
+        ref_res = res0.clone()
+        ops.fused_add_rms_norm(ref_h, ref_res, w, 1e-5)
+        if mode in ("nvls", "nvls-p2p"):
+            nvls.x(batch).copy_(x)
+            res = res0.clone()
+            h = nvls.allreduce_add_rms_norm(batch, res, w, 1e-5)
+            torch.cuda.synchronize()
+            lo, hi = nvls.rows_of(env.rank, batch)
+            ok = ok and torch.equal(h, ref_h) and torch.equal(res[lo:hi], ref_res[lo:hi])
+        else:
+            out = ca.custom_all_reduce(x)
+            res = res0.clone()
+            ops.fused_add_rms_norm(out, res, w, 1e-5)
+            torch.cuda.synchronize()
+            ok = ok and torch.equal(out, ref_h) and torch.equal(res, ref_res)
+    return env.all_agree(bool(ok))
+
+
+def setup_exchange(env, args, hidden, dtype):
+    """Chooses the TP exchange implementation. Returns (mode, nvls, ca, parity_report)."""
+    if env.world == 1:
+        return "none", None, None, None
+    order = {"auto": ["nvls", "nvls-p2p", "p2p", "nccl"], "nvls": ["nvls"], "nvls-p2p": ["nvls-p2p"], "p2p": ["p2p"],
+             "nccl": ["nccl"]}[args.allreduce]
+    report = {}
+    for mode in order:
+        if mode == "nccl":
+            report[mode] = "reference"
+            return mode, None, None, report
+        nvls = ca = None
+        why = None
+        try:
+            if mode in ("nvls", "nvls-p2p"):
+                from aphrodite_engine_b200.distributed.nvls import NvlsTensorParallel
+                nvls = NvlsTensorParallel(env.group, env.dev, args.batch, hidden, dtype, use_multicast=(mode == "nvls"))
+                if mode == "nvls" and not nvls.multicast:
+                    why = "no multicast mapping on this box"
+            else:
+                from aphrodite_engine_b200.distributed import CustomAllreduce
+                ca = CustomAllreduce(env.cpu_group, env.dev)
+                if ca.disabled:
+                    why = "peer access unavailable"
+        except Exception as e:          # keep measuring with the next implementation, and say so
+            why = f"setup failed: {e!r}"[:200]
+        if not env.all_agree(why is None):
+            report[mode] = why or "unavailable on another rank"
+            env.log(f"exchange '{mode}' not used: {report[mode]}")
+            continue
+        if exchange_parity_exact(env, mode, nvls, ca, args.batch, hidden, dtype):
+            report[mode] = "ok"
+            return mode, nvls, ca, report
+        report[mode] = "FAILED exact parity vs NCCL + fused_add_rms_norm"
+        env.log(f"exchange '{mode}' FAILED its parity check; falling back")
+    raise SystemExit(f"no usable TP exchange: {report}")
+
+
+def capture(env, model, st, ca=None):
+    """CUDA graph of one decode step (None if capture fails: the caller then measures eagerly and says so)."""
+    if env.args.no_graph:
+        return None
+    try:
+        graph = torch.cuda.CUDAGraph()
+        with (ca.capture() if ca is not None else contextlib.nullcontext()):
+            with torch.cuda.graph(graph, stream=env.stream):
+                model.forward(st)
+        return graph
+    except Exception as e:
+        env.log(f"CUDA graph capture failed ({e}); running eagerly")
+        torch.cuda.synchronize()
+        return None
+
+
+def time_steps(env, step, K, W, sampler=None):
+    """W warm-up steps, then K timed steps: one event bracket (the contract's number) + an event after every step.
+    Returns (ms_per_step = max over ranks of bracket / K, per-step stats of this rank)."""
+    stream = env.stream
+    for _ in range(W):
+        step()
+    env.barrier()
+    if sampler is not None:
+        sampler.mark()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+    evs[0].record(stream)
+    for i in range(K):
+        step()
+        evs[i + 1].record(stream)
+    env.barrier()
+    total = evs[0].elapsed_time(evs[K])
+    per = [evs[i].elapsed_time(evs[i + 1]) for i in range(K)]
+    stats = {"median": statistics.median(per), "min": min(per), "max": max(per)}
+    return env.max_over_ranks(total) / K, stats
+
+
 def run_b200(args):
     # keep stdout to exactly ONE JSON line: libraries (NCCL prints its version banner) write to fd 1 too
     real_stdout = os.dup(1)
     os.dup2(2, 1)
     os.environ.setdefault("NCCL_DEBUG", "WARN")
-    import torch.distributed as dist
     from aphrodite_engine_b200.llama_decode import (DecodeState, LlamaDecoder, LlamaShape,
                                                     make_synthetic_batch, upload)
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node == --gpus"
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    group, ca = None, None
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-        group = dist.group.WORLD
-        if args.allreduce == "custom" or (args.allreduce == "auto" and world <= 4):
-            from aphrodite_engine_b200.distributed import CustomAllreduce
-            ca = CustomAllreduce(dist.new_group(backend="gloo"), dev)
-            if ca.disabled:
-                ca = None
+    env = Env(args)
+    world, rank, dev, dist, stream = env.world, env.rank, env.dev, env.dist, env.stream
+    sampler = ClockSampler(env.local)
+    if rank == 0:
+        sampler.start()          # before any timed work: its start-up cost falls into model construction
 
     shape = LlamaShape(layers=args.layers)
+    dtype = torch.bfloat16
+    mode, nvls, ca, parity = setup_exchange(env, args, shape.hidden, dtype)
     host, num_blocks = make_synthetic_batch(args.batch, args.ctx, args.block_size)
-    model = LlamaDecoder(shape, args.batch, args.block_size, num_blocks, dev, torch.bfloat16,
-                         args.kv_cache_dtype, tp_rank=rank, tp_size=world, group=group, quant=args.quant, custom_ar=ca)
+    model = LlamaDecoder(shape, args.batch, args.block_size, num_blocks, dev, dtype,
+                         args.kv_cache_dtype, tp_rank=rank, tp_size=world, group=env.group, quant=args.quant,
+                         custom_ar=ca, nvls=nvls)
     st = DecodeState(args.batch, host["block_tables"].shape[1], dev)
     h2d_bytes = upload(st, host)
     torch.cuda.synchronize()
 
-    stream = torch.cuda.Stream(device=dev)
-    graph = None
+    tp_parity = None
     with torch.cuda.stream(stream):
         for _ in range(2):                   # eager warm-up (cuBLAS workspaces, NCCL channels)
             model.forward(st)
         stream.synchronize()
-        if not args.no_graph:
-            try:
-                import contextlib
-                graph = torch.cuda.CUDAGraph()
-                with (ca.capture() if ca is not None else contextlib.nullcontext()):
-                    with torch.cuda.graph(graph, stream=stream):
-                        model.forward(st)
-            except Exception as e:       # keep measuring, eagerly, and say so
-                graph = None
-                if rank == 0:
-                    print(f"[bench] CUDA graph capture failed ({e}); running eagerly", file=sys.stderr)
-                torch.cuda.synchronize()
+        if world > 1:
+            # whole-step check of the exchange in use against the NCCL exchange: same weights, same cache, eager
+            tp_parity = {"exchange": mode, "exact_small_int_vs_nccl_plus_norm": parity}
+            if mode != "nccl":
+                twin = LlamaDecoder(shape, args.batch, args.block_size, num_blocks, dev, dtype, args.kv_cache_dtype,
+                                    tp_rank=rank, tp_size=world, group=env.group, quant=args.quant, share_from=model)
+                model.forward(st)
+                h_a, t_a = model.last_hidden.float().clone(), st.next_tokens.clone()
+                twin.forward(st)
+                h_b, t_b = twin.last_hidden.float(), st.next_tokens.clone()
+                stream.synchronize()
+                rel = float((h_a - h_b).norm() / h_b.norm().clamp_min(1e-30))
+                tp_parity["step_vs_nccl"] = {
+                    "hidden_rel_fro_err": rel, "hidden_max_abs_err": float((h_a - h_b).abs().max()),
+                    "token_agreement": float((t_a == t_b).float().mean()),
+                    "tolerance": "rel_fro_err <= 2e-2 (bf16, 64 differently-rounded reductions per step)",
+                    "ok": env.all_agree(rel <= 2e-2)}
+                del twin, h_a, h_b
+            tp_parity["ok"] = all(v in ("ok", "reference") or not str(v).startswith("FAILED")
+                                  for v in (parity or {}).values()) and \
+                tp_parity.get("step_vs_nccl", {}).get("ok", True)
+        graph = capture(env, model, st, ca)
 
     def step():
         if graph is not None:
@@ -310,51 +501,28 @@ def run_b200(args):
         else:
             model.forward(st)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(ms):
-        if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            return float(t.item())
-        return ms
-
-    K, W = args.steps, max(args.warmup, 3)
-    sampler = ClockSampler(local)
+    K = args.steps
+    W = max(args.warmup, 3) if world == 1 else max(args.warmup, 20)   # a graph holding a collective needs more replays to settle
+    remeasured = False
     with torch.cuda.stream(stream):
         # ---------------- leg 1: device-resident ----------------
-        for _ in range(W):
-            step()
-        barrier()
-        if rank == 0:
-            sampler.start()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for _ in range(K):
-            step()
-        e1.record(stream)
-        barrier()
+        ms_dev, per_step = time_steps(env, step, K, W, sampler if rank == 0 else None)
+        if env.all_agree(ms_dev <= 1.10 * per_step["median"]) is False:
+            # something stalled inside the bracket (a step far above the median): measure once more, keep both
+            first = {"ms_per_step": ms_dev, "per_step_ms": per_step}
+            ms_dev, per_step = time_steps(env, step, K, 3, sampler if rank == 0 else None)
+            remeasured = first
         clocks = sampler.stop() if rank == 0 else None
-        ms_dev = max_over_ranks(e0.elapsed_time(e1)) / K
 
         # ---------------- leg 2: end to end from host buffers ----------------
         out_host = torch.empty(args.batch, dtype=torch.long).pin_memory()
-        for _ in range(W):
-            upload(st, host); step(); out_host.copy_(st.next_tokens, non_blocking=True); stream.synchronize()
-        barrier()
-        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e2.record(stream)
-        for _ in range(K):
+
+        def e2e_step():
             upload(st, host)
             step()
             out_host.copy_(st.next_tokens, non_blocking=True)
             stream.synchronize()             # the sampled tokens are needed on the host every step
-        e3.record(stream)
-        barrier()
-        ms_e2e = max_over_ranks(e2.elapsed_time(e3)) / K
+        ms_e2e, e2e_per_step = time_steps(env, e2e_step, K, 3)
         d2h_bytes = out_host.numel() * out_host.element_size()
 
         # ---------------- leg 3: attention launches timed inside eager steps ----------------
@@ -395,32 +563,59 @@ def run_b200(args):
     }
     traffic_file = os.path.join(ROOT, "profiles", "attention_traffic.json")
     if os.path.exists(traffic_file) and world == 1 and (args.batch, args.ctx, args.block_size, args.kv_cache_dtype) == (256, 4096, 16, "auto"):
-        try:
+        try:  # not re-measured in this run: the dram__bytes of the committed `ncu --set full` capture of this kernel/shape
             roofline["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")
+            roofline["traffic_source"] = "profiles/attention_traffic.json (ncu capture, constant; not re-measured per run)"
         except Exception:
             pass
+    weight_bytes = 2 * (8.03e9 - 0.525e9)
+    step_bytes = (algo_bytes * shape.layers + weight_bytes / world)
+    roofline["whole_step"] = {"algorithmic_bytes_per_gpu": step_bytes,
+                              "frac_of_hbm_peak": step_bytes / (ms_dev * 1e-3) / 1e9 / peaks["hbm_gbs"]}
 
     line = {
         "metric": METRIC, "value": args.batch / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world,
-        "steps": K, "warmup": W, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "steps": K, "warmup": W, "ms_per_step": ms_dev, "per_step_ms": per_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"Llama-3-8B bf16 paged-attention decode bs={args.batch} ctx={args.ctx} "
                                f"block={args.block_size} layers={shape.layers} "
                                + ("GPTQ int4 Marlin W4A16 linears (BASELINE configs[2])" if args.quant else "(BASELINE configs[1])"),
-                   "parallelism": f"tp{world}", "allreduce": ("nvlink-p2p" if ca is not None else ("nccl" if world > 1 else "none")), "kv_cache_dtype": args.kv_cache_dtype,
+                   "parallelism": f"tp{world}", "allreduce": {"none": "none", "nvls": "nvls-fused (multimem reduce + add + rms_norm)",
+                                                              "nvls-p2p": "fused kernel over unicast peer pointers",
+                                                              "p2p": "nvlink-p2p", "nccl": "nccl"}[mode],
+                   "kv_cache_dtype": args.kv_cache_dtype,
                    "cuda_graph": graph is not None, "l2": "working set (KV + weights) >> 126 MB L2, no flush needed"},
         "e2e": {"value": args.batch / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
-                "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e},
+                "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e, "per_step_ms": e2e_per_step},
         "gpu_launches": model.my_kernel_launches_per_step * K,
         "roofline": roofline, "clocks": clocks,
     }
+    if remeasured:
+        line["remeasured_after_stall"] = remeasured
+    if tp_parity is not None:
+        line["tp_parity"] = tp_parity
+        line["allreduce_parity"] = "ok" if tp_parity["ok"] else "FAILED"
+
+    # ---------------- reference CUDA kernels, same step, same graph treatment ----------------
+    if not args.no_ref_cuda:
+        try:
+            line["ref_cuda"] = ref_cuda_leg(env, args, model, st, shape, num_blocks, dtype, ms_dev, K)
+        except Exception as e:
+            line["ref_cuda"] = {"unavailable": repr(e)[:300]}
+    if not args.no_secondary:
+        try:
+            line["secondary"] = secondary_legs(env, args, model, st, host, shape, num_blocks, dtype, peaks)
+        except Exception as e:
+            line["secondary"] = {"error": repr(e)[:300]}
+
     if world == 1 and not args.no_cpu_baseline:
         del model
         torch.cuda.empty_cache()
         try:
-            val, step_s, kind, cores, desc = cpu_reference_sample(args, args.cpu_sample_layers, 2, 1)
-            line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc,
-                                    "s_per_step": step_s}
+            r = cpu_reference_sample(args, args.cpu_sample_layers, 2, 1)
+            line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+                                    "sample": r["sample"], "s_per_step": r["step_s"], "layer_ms": r["layer_ms"],
+                                    "host_loadavg_1m": r["host_loadavg_1m"]}
         except Exception as e:  # never lose the GPU numbers to a host-side problem
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "error": repr(e)}
     if rank == 0:
@@ -433,6 +628,66 @@ def run_b200(args):
         sys.stdout.flush()
         sys.stderr.flush()
         os._exit(0)
+
+
+def ref_cuda_leg(env, args, model, st, shape, num_blocks, dtype, ms_mine, K):
+    """The same decode step over the reference's own CUDA kernels (recompiled for sm_100a): same weights and KV
+    cache (share_from), the reference's op sequence (aphrodite/modeling/models/llama.py:234-261), its V1/V2 rule, its
+    custom all-reduce kernel at N > 1 (NCCL if that cannot be set up), cuBLAS GEMMs, CUDA-graph replay."""
+    from oracle import ref_cuda_ops as rco
+    from aphrodite_engine_b200.llama_decode import LlamaDecoder
+    if not rco.available():
+        return {"unavailable": "oracle/_ref/_ref_cuda_C.so not built"}
+    table = rco.RefCudaOps()
+    ref_ca, ar = None, "none"
+    if env.world > 1:
+        ar = "nccl"
+        ok = True
+        try:
+            ref_ca = rco.make_custom_allreduce(env.cpu_group, env.dev, table)
+            ok = not ref_ca.disabled
+        except Exception as e:
+            env.log(f"reference custom all-reduce unavailable ({e!r}); its leg uses NCCL")
+            ok = False
+        if env.all_agree(ok):
+            ar = "reference custom_all_reduce kernel"
+        else:
+            ref_ca = None
+    ref_model = LlamaDecoder(shape, args.batch, args.block_size, num_blocks, env.dev, dtype, args.kv_cache_dtype,
+                             tp_rank=env.rank, tp_size=env.world, group=env.group, quant=args.quant,
+                             custom_ar=ref_ca, op_table=table, attention_cls=rco.make_attention_cls(table),
+                             share_from=model)
+    with torch.cuda.stream(env.stream):
+        model.forward(st)
+        h_mine = model.last_hidden.float().clone()
+        for _ in range(2):
+            ref_model.forward(st)
+        h_ref = ref_model.last_hidden.float()
+        env.stream.synchronize()
+        rel = float((h_mine - h_ref).norm() / h_ref.norm().clamp_min(1e-30))
+        graph = capture(env, ref_model, st, ref_ca)
+
+        def step():
+            if graph is not None:
+                graph.replay()
+            else:
+                ref_model.forward(st)
+        Kr = max(5, min(K, 20))
+        ms_ref, per = time_steps(env, step, Kr, 3 if env.world == 1 else 10)
+    return {"value": args.batch / (ms_ref * 1e-3), "unit": UNIT, "ms_per_step": ms_ref, "per_step_ms": per, "steps": Kr,
+            "ratio": ms_ref / ms_mine, "ratio_meaning": "this repo's tok/s / reference-CUDA-kernels tok/s (>= 1.0 is the target)",
+            "allreduce": ar, "cuda_graph": graph is not None,
+            "hidden_rel_fro_err_vs_this_repo": rel,
+            "kernels": "reference kernels/*.cu compiled for sm_100a by oracle/build_ref_cuda.py; GEMMs cuBLAS in both arms"}
+
+
+def secondary_legs(env, args, model, st, host, shape, num_blocks, dtype, peaks):
+    """BASELINE configs[2..4] as bounded legs. Filled in by bench_secondary.py when present."""
+    try:
+        import bench_secondary
+    except ImportError:
+        return {"note": "bench_secondary.py not present"}
+    return bench_secondary.run(env, args, model, st, host, shape, num_blocks, dtype, peaks)
 
 
 def main():

@@ -231,6 +231,28 @@ int b200_car_get_graph_buffer_ipc_meta(int64_t fa, void* handles_out, int64_t* o
 /* handles: [world_size][n] x 64 bytes, offsets: [world_size][n] */
 int b200_car_register_graph_buffers(int64_t fa, const void* handles, const int64_t* offsets, int n);
 
+/* ---- fused tensor-parallel exchange over NVSwitch multicast (B200 design) ----------------
+ * replaces the SEQUENCE  all_reduce (kernels/all_reduce/custom_all_reduce.cuh:183-249, called from
+ *          aphrodite/distributed/parallel_state.py:353-379 after every row-parallel linear)
+ *          -> fused_add_rms_norm (kernels/layernorm_kernels.cu:204-286, aphrodite/modeling/models/llama.py:250-256)
+ * with one kernel. Every rank owns one SYMMETRIC allocation (same layout on all ranks) that is mapped on every peer
+ * (`peer_bases[world]`, unicast VAs as int64; peer_bases[rank] == local_base) and, when the fabric supports it, bound
+ * to one multicast object mapped at `mc_base` (NULL: the unicast peer-pointer variant of the same algorithm runs).
+ * Inside the allocation, at byte offsets: `in_off` the rank's partial sums X [num_tokens, hidden] (the row-parallel
+ * GEMM's output), `out_off` the result H [num_tokens, hidden] (identical on all ranks afterwards), `flag_off`
+ * b200_tp_flag_bytes() bytes of barrier state, ZERO before the first call (and a host barrier after zeroing).
+ * residual/weight != NULL: H = rms_norm(sum_r X_r + residual) * weight with the reference's rounding points, and
+ * residual <- sum + residual for THIS RANK'S rows only, rows [rank*ceil(T/world), ...) — the residual stream is
+ * token-sharded across ranks (each row is owned by one rank for the whole forward pass).
+ * residual == weight == NULL: H = sum_r X_r (plain all-reduce, fp32 accumulate, one rounding).
+ * fp16 / bf16, hidden % 8 == 0, hidden <= 16384. Stream-ordered, no host state: CUDA-graph capturable. Every rank
+ * must issue the same sequence of calls (the barriers pair launches by order). */
+int64_t b200_tp_flag_bytes(void);
+int b200_tp_allreduce_rows(void* mc_base, void* local_base, const int64_t* peer_bases, int64_t in_off,
+                           int64_t out_off, int64_t flag_off, void* residual, const void* weight,
+                           float epsilon, int num_tokens, int hidden, int rank, int world, int dtype,
+                           void* stream);
+
 /* ---- small adjacent ops ------------------------------------------------------------------------------
  * replaces permute_cols            kernels/permute_cols.cu (schema torch_bindings.cpp:218-219): out[m,k] = a[m,perm[k]]
  *          awq_dequantize          kernels/quantization/awq/gemm_kernels.cu:720-780 (schema :147-151), fp16 only

@@ -12,7 +12,7 @@ translation units with nvcc directly — not the reference's CMake build, which 
     attention/attention_kernels.cu  cache_kernels.cu  layernorm_kernels.cu  pos_encoding_kernels.cu
     activation_kernels.cu  permute_cols.cu  prepare_inputs/advance_step.cu
     quantization/gptq_marlin/{gptq_marlin,gptq_marlin_repack,awq_marlin_repack}.cu  quantization/awq/gemm_kernels.cu
-    moe/{align_block_size_kernel,softmax,marlin_moe_ops}.cu
+    moe/{align_block_size_kernel,softmax,marlin_moe_ops}.cu  all_reduce/custom_all_reduce.cu
 
 with the flags of cmake/utils.cmake:93-111 (torch's COMMON_NVCC_FLAGS minus the __CUDA_NO_HALF* set, -DENABLE_FP8)
 and `-gencode arch=compute_100a,code=sm_100a`. Registration: oracle/ref_cuda_bindings.cpp (namespace _ref_cuda_C).
@@ -47,6 +47,9 @@ CU_SRCS = [
     "moe/softmax.cu",
     "moe/marlin_moe_ops.cu",
 ]
+# the reference's own TP all-reduce (the N > 1 legs of bench.py's ref_cuda arm): its own library, it needs libcuda
+AR_SRC = "all_reduce/custom_all_reduce.cu"
+AR_TARGET = os.path.join(OUT, "_ref_cuda_ar_C.so")
 
 
 def _run(cmd):
@@ -61,7 +64,9 @@ def _run(cmd):
 def build(force: bool = False) -> bool:
     """Returns True if oracle/_ref/_ref_cuda_C.so exists afterwards."""
     bind_src = os.path.join(HERE, "ref_cuda_bindings.cpp")
-    fresh = os.path.exists(TARGET) and os.path.getmtime(TARGET) >= os.path.getmtime(bind_src)
+    ar_bind_src = os.path.join(HERE, "ref_cuda_ar_bindings.cpp")
+    fresh = (os.path.exists(TARGET) and os.path.getmtime(TARGET) >= os.path.getmtime(bind_src) and
+             os.path.exists(AR_TARGET) and os.path.getmtime(AR_TARGET) >= os.path.getmtime(ar_bind_src))
     if fresh and not force:
         return True
     if not os.path.isdir(os.path.join(REF, "kernels", "attention")):
@@ -87,12 +92,21 @@ def build(force: bool = False) -> bool:
             jobs.append(cu + ["-c", os.path.join(REF, "kernels", s), "-o", obj])
     bind_obj = os.path.join(objdir, "ref_cuda_bindings.o")
     jobs.append(["g++", "-std=c++17", "-O2", "-fPIC", "-w", *defs, *inc, "-c", bind_src, "-o", bind_obj])
+    ar_obj = os.path.join(objdir, AR_SRC.replace("/", "_").replace(".cu", ".o"))
+    if force or not os.path.exists(ar_obj):
+        jobs.append(cu + ["-c", os.path.join(REF, "kernels", AR_SRC), "-o", ar_obj])
+    ar_bind_obj = os.path.join(objdir, "ref_cuda_ar_bindings.o")
+    ar_defs = [d.replace("_ref_cuda_C", "_ref_cuda_ar_C") for d in defs]
+    jobs.append(["g++", "-std=c++17", "-O2", "-fPIC", "-w", *ar_defs, *inc, "-c", ar_bind_src, "-o", ar_bind_obj])
     with ThreadPoolExecutor(max_workers=max(1, min(8, (os.cpu_count() or 2) // 2))) as ex:
         for cmd, dt in zip(jobs, ex.map(_run, jobs)):
             print(f"  built {os.path.basename(cmd[-1])} in {dt:.0f}s", flush=True)
     _run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", *objs, bind_obj, f"-L{tdir}/lib",
           "-ltorch", "-ltorch_cpu", "-ltorch_cuda", "-lc10", "-lc10_cuda", "-ltorch_python",
           "-Xlinker", f"-rpath={tdir}/lib", "-o", TARGET])
+    _run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", ar_obj, ar_bind_obj, f"-L{tdir}/lib",
+          "-ltorch", "-ltorch_cpu", "-ltorch_cuda", "-lc10", "-lc10_cuda", "-ltorch_python",
+          "-L/usr/local/cuda/lib64/stubs", "-lcuda", "-Xlinker", f"-rpath={tdir}/lib", "-o", AR_TARGET])
     return True
 
 

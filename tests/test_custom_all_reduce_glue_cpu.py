@@ -60,6 +60,7 @@ class _Torch:
 def _make(monkeypatch, world, rank, peers_ok=True, **kw):
     ops, tp = _Ops(), _Torch(peers_ok)
     monkeypatch.setattr(car, "ops", ops)
+    monkeypatch.setattr(car.CustomAllreduce, "_ops", ops)
     monkeypatch.setattr(car, "torch", tp)
 
     def bcast(lst, src, group=None, device=None):

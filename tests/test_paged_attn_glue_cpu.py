@@ -21,6 +21,7 @@ class _Recorder:
 def rec(monkeypatch):
     r = _Recorder()
     monkeypatch.setattr(pa, "ops", r)
+    monkeypatch.setattr(pa.PagedAttention, "_ops", r)
     return r
 
 
