@@ -44,9 +44,12 @@ SIGNATURES = {
     "b200_rms_norm": [c_void_p] * 3 + [c_float] + [c_int] * 3 + [c_void_p],
     "b200_fused_add_rms_norm": [c_void_p] * 3 + [c_float] + [c_int] * 3 + [c_void_p],
     "b200_rotary_embedding": [c_void_p] * 5 + [c_int] * 5 + [c_int64] * 2 + [c_int] * 2 + [c_void_p],
+    "b200_rotary_embedding_and_cache": [c_void_p] * 8 + [c_int] * 5 + [c_int64] * 3 + [c_int] * 5 + [c_float] * 2 +
+                                       [c_void_p],
     "b200_act_and_mul": [c_void_p] * 2 + [c_int] * 4 + [c_void_p],
     "b200_activation": [c_void_p] * 2 + [c_int] * 4 + [c_void_p],
     "b200_marlin_gemm_plan": [c_int] * 4,
+    "b200_marlin_dense_plan": [c_int] * 4 + [c_void_p],
     "b200_debug_marlin_prof": [c_void_p],
     "b200_gptq_marlin_gemm": [c_void_p] * 7 + [c_int] * 8 + [c_void_p],
     "b200_marlin_gemm_moe": [c_void_p] * 3 + [c_int64] + [c_void_p] * 7 + [c_int] * 10 + [c_void_p],
@@ -66,7 +69,7 @@ SIGNATURES = {
     "b200_car_register_graph_buffers": [c_int64, c_void_p, c_void_p, c_int],
     "b200_tp_flag_bytes": [],
     "b200_tp_allreduce_rows": [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p,
-                               c_float] + [c_int] * 5 + [c_void_p],
+                               c_float] + [c_int] * 6 + [c_void_p],
     "b200_get_device_attribute": [c_int64, c_int64],
     "b200_get_max_shared_memory_per_block_device_attribute": [c_int64],
 }

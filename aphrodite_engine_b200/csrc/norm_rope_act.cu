@@ -182,6 +182,93 @@ rotary_kernel(const int64_t* __restrict__ positions, T* __restrict__ query, T* _
 }
 
 // ------------------------------------------------------------------------------------------------
+// rotary_embedding + reshape_and_cache in ONE launch (decode: both are latency-bound singletons).
+// Same outputs as the two reference kernels run back to back (pos_encoding_kernels.cu:71-93 then
+// cache_kernels.cu:152-204): q and k rotated in place, the ROTATED k and v scattered to slot_mapping[t].
+// Flat grid over (token, {q heads | k heads | v heads}, 16-byte chunk). NeoX style, rot_dim == head_size.
+// ------------------------------------------------------------------------------------------------
+template <typename T, int KV>
+__global__ void __launch_bounds__(256)
+rope_and_cache_kernel(const int64_t* __restrict__ positions, T* __restrict__ query, T* __restrict__ key,
+                      const T* __restrict__ value, const T* __restrict__ cache, void* __restrict__ key_cache,
+                      void* __restrict__ value_cache, const int64_t* __restrict__ slot_mapping, int num_tokens,
+                      int num_heads, int num_kv_heads, int head_size, int64_t q_stride, int64_t k_stride,
+                      int64_t v_stride, int block_size, int x, float k_scale, float v_scale) {
+  constexpr int N = Vec16<T>::N;                      // 8 elements per 16-byte vector (16-bit types only)
+  const int embed = head_size / 2;
+  const int rc = embed / N;                           // rotary chunks per head (each = N pairs)
+  const int vcn = head_size / N;                      // value chunks per head
+  const int q_items = num_heads * rc, k_items = num_kv_heads * rc, v_items = num_kv_heads * vcn;
+  const int per_tok = q_items + k_items + v_items;
+  const int64_t total = (int64_t)num_tokens * per_tok;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t tok = idx / per_tok;
+    int r = (int)(idx % per_tok);
+    if (r < q_items + k_items) {
+      const bool is_k = r >= q_items;
+      if (is_k) r -= q_items;
+      const int h = r / rc, c = r % rc;
+      const int64_t pos = positions[tok];
+      const T* cosp = cache + pos * head_size;
+      const T* sinp = cosp + embed;
+      T* arr = is_k ? key + tok * k_stride + (int64_t)h * head_size : query + tok * q_stride + (int64_t)h * head_size;
+      const int p0 = c * N;
+      Vec16<T> xv, yv, cs, sn;
+      xv.raw = *reinterpret_cast<const uint4*>(arr + p0);
+      yv.raw = *reinterpret_cast<const uint4*>(arr + embed + p0);
+      cs.raw = __ldg(reinterpret_cast<const uint4*>(cosp + p0));
+      sn.raw = __ldg(reinterpret_cast<const uint4*>(sinp + p0));
+#pragma unroll
+      for (int e = 0; e < N; ++e) rot_pair<T>(xv.e[e], yv.e[e], cs.e[e], sn.e[e]);
+      *reinterpret_cast<uint4*>(arr + p0) = xv.raw;
+      *reinterpret_cast<uint4*>(arr + embed + p0) = yv.raw;
+      if (is_k) {
+        const int64_t slot = slot_mapping[tok];
+        if (slot >= 0) {
+          const int64_t blk = slot / block_size, boff = slot % block_size;
+          const int64_t hb = (blk * num_kv_heads + h) * (head_size / x);
+          if constexpr (KV == B200_KV_AUTO) {
+            T* kc = reinterpret_cast<T*>(key_cache);      // x == N: one 16-byte run per chunk
+            *reinterpret_cast<uint4*>(kc + ((hb + p0 / x) * block_size + boff) * x) = xv.raw;
+            *reinterpret_cast<uint4*>(kc + ((hb + (embed + p0) / x) * block_size + boff) * x) = yv.raw;
+          } else {
+            uint8_t* kc = reinterpret_cast<uint8_t*>(key_cache);
+            union { uint2 raw; uint8_t b[8]; } qx, qy;
+#pragma unroll
+            for (int e = 0; e < N; ++e) {
+              qx.b[e] = fp8_quant<T, KV>(xv.e[e], k_scale);
+              qy.b[e] = fp8_quant<T, KV>(yv.e[e], k_scale);
+            }
+            // x == 16 cache bytes per run; an 8-element chunk is half a run (8-byte aligned)
+            *reinterpret_cast<uint2*>(kc + ((hb + p0 / x) * block_size + boff) * x + p0 % x) = qx.raw;
+            *reinterpret_cast<uint2*>(kc + ((hb + (embed + p0) / x) * block_size + boff) * x + (embed + p0) % x) = qy.raw;
+          }
+        }
+      }
+    } else {
+      r -= q_items + k_items;
+      const int64_t slot = slot_mapping[tok];
+      if (slot < 0) continue;
+      const int h = r / vcn, c = r % vcn;
+      const int64_t blk = slot / block_size, boff = slot % block_size;
+      Vec16<T> vv;
+      vv.raw = __ldg(reinterpret_cast<const uint4*>(value + tok * v_stride + (int64_t)h * head_size + c * N));
+      const int64_t dst = ((blk * num_kv_heads + h) * head_size + c * N) * block_size + boff;
+      if constexpr (KV == B200_KV_AUTO) {
+        T* vc = reinterpret_cast<T*>(value_cache);
+#pragma unroll
+        for (int e = 0; e < N; ++e) vc[dst + (int64_t)e * block_size] = vv.e[e];
+      } else {
+        uint8_t* vc = reinterpret_cast<uint8_t*>(value_cache);
+#pragma unroll
+        for (int e = 0; e < N; ++e) vc[dst + (int64_t)e * block_size] = fp8_quant<T, KV>(vv.e[e], v_scale);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Activations
 // ------------------------------------------------------------------------------------------------
 enum { ACT_SILU = 0, ACT_GELU = 1, ACT_GELU_TANH = 2 };
@@ -357,6 +444,48 @@ extern "C" int b200_rotary_embedding(const int64_t* positions, void* query, void
   B200_DISPATCH_T(dtype, FN);
 #undef FN
   return check_launch("rotary_kernel");
+}
+
+extern "C" int b200_rotary_embedding_and_cache(const int64_t* positions, void* query, void* key, const void* value,
+                                               const void* cos_sin_cache, void* key_cache, void* value_cache,
+                                               const int64_t* slot_mapping, int num_tokens, int num_heads,
+                                               int num_kv_heads, int head_size, int rot_dim, int64_t query_stride,
+                                               int64_t key_stride, int64_t value_stride, int is_neox, int block_size,
+                                               int x, int dtype, int kv_dtype, float k_scale, float v_scale,
+                                               void* stream) {
+  B200_CHECK(dtype >= B200_F32 && dtype <= B200_BF16, "rotary_embedding_and_cache: unsupported dtype");
+  B200_CHECK(kv_dtype >= B200_KV_AUTO && kv_dtype <= B200_KV_FP8_E5M2, "rotary_embedding_and_cache: bad kv_cache_dtype");
+  if (num_tokens == 0) return 0;
+  const bool aligned =
+      ((reinterpret_cast<uintptr_t>(query) | reinterpret_cast<uintptr_t>(key) | reinterpret_cast<uintptr_t>(value) |
+        reinterpret_cast<uintptr_t>(cos_sin_cache) | reinterpret_cast<uintptr_t>(key_cache)) & 15) == 0 &&
+      (query_stride % 8) == 0 && (key_stride % 8) == 0 && (value_stride % 8) == 0;
+  const bool fused = dtype != B200_F32 && is_neox && rot_dim == head_size && head_size % 16 == 0 && aligned &&
+                     x == (kv_dtype == B200_KV_AUTO ? 8 : 16);
+  if (!fused) {   // any other configuration: the two kernels back to back (identical results by definition)
+    int rc = b200_rotary_embedding(positions, query, key, cos_sin_cache, nullptr, num_tokens, num_heads, num_kv_heads,
+                                   head_size, rot_dim, query_stride, key_stride, is_neox, dtype, stream);
+    if (rc != 0) return rc;
+    return b200_reshape_and_cache(key, value, key_cache, value_cache, slot_mapping, num_tokens, num_kv_heads, head_size,
+                                  block_size, x, key_stride, value_stride, dtype, kv_dtype, k_scale, v_scale, stream);
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int per_tok = (num_heads + num_kv_heads) * (head_size / 16) + num_kv_heads * (head_size / 8);
+  const int grid = flat_grid((int64_t)num_tokens * per_tok);
+#define B200_RC(T, KVD)                                                                                          \
+  rope_and_cache_kernel<T, KVD><<<grid, 256, 0, st>>>(positions, (T*)query, (T*)key, (const T*)value,             \
+      (const T*)cos_sin_cache, key_cache, value_cache, slot_mapping, num_tokens, num_heads, num_kv_heads, head_size, \
+      query_stride, key_stride, value_stride, block_size, x, k_scale, v_scale)
+#define B200_RC_T(T)                                              \
+  do {                                                            \
+    if (kv_dtype == B200_KV_AUTO) B200_RC(T, B200_KV_AUTO);       \
+    else if (kv_dtype == B200_KV_FP8_E4M3) B200_RC(T, B200_KV_FP8_E4M3); \
+    else B200_RC(T, B200_KV_FP8_E5M2);                            \
+  } while (0)
+  if (dtype == B200_BF16) B200_RC_T(__nv_bfloat16); else B200_RC_T(__half);
+#undef B200_RC_T
+#undef B200_RC
+  return check_launch("rope_and_cache_kernel");
 }
 
 extern "C" int b200_act_and_mul(void* out, const void* input, int num_tokens, int d, int act,

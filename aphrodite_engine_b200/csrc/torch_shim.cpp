@@ -584,7 +584,7 @@ void register_graph_buffers(fptr_t fa, const std::vector<std::string>& handles,
 void tp_allreduce_rows(int64_t mc_base, torch::Tensor& block, const std::vector<int64_t>& peer_bases,
                        torch::Tensor& x, torch::Tensor& out, const c10::optional<torch::Tensor>& residual,
                        const c10::optional<torch::Tensor>& weight, double epsilon, int64_t flag_off, int64_t rank,
-                       int64_t world) {
+                       int64_t world, int64_t algo) {
   const at::cuda::OptionalCUDAGuard guard(device_of(block));
   TORCH_CHECK(x.dim() == 2 && x.is_contiguous() && out.is_contiguous() && x.sizes() == out.sizes() &&
               x.scalar_type() == out.scalar_type(), "tp_allreduce_rows: x / out must be contiguous [T, H] of one dtype");
@@ -604,7 +604,27 @@ void tp_allreduce_rows(int64_t mc_base, torch::Tensor& block, const std::vector<
   check(b200_tp_allreduce_rows(reinterpret_cast<void*>(mc_base), base, peer_bases.data(), in_off, out_off, flag_off,
                                residual ? residual->data_ptr() : nullptr, weight ? weight->data_ptr() : nullptr,
                                (float)epsilon, (int)x.size(0), (int)x.size(1), (int)rank, (int)world,
-                               dtype_code(x, "tp_allreduce_rows"), cur_stream()));
+                               dtype_code(x, "tp_allreduce_rows"), (int)algo, cur_stream()));
+}
+// rotary_embedding + reshape_and_cache in one launch (csrc/norm_rope_act.cu). query [T, Hq*D], key / value [T, Hkv*D]
+// (views of the qkv GEMM output); caches in the reference's paged layout.
+void rotary_embedding_and_cache(torch::Tensor& positions, torch::Tensor& query, torch::Tensor& key,
+                                torch::Tensor& value, int64_t head_size, torch::Tensor& cos_sin_cache, bool is_neox,
+                                torch::Tensor& key_cache, torch::Tensor& value_cache, torch::Tensor& slot_mapping,
+                                const std::string& kv_cache_dtype, double k_scale, double v_scale) {
+  const at::cuda::OptionalCUDAGuard guard(device_of(query));
+  const int64_t num_tokens = query.numel() / query.size(-1);
+  TORCH_CHECK(key.size(-1) == value.size(-1) && key.scalar_type() == query.scalar_type() &&
+              value.scalar_type() == query.scalar_type(), "rotary_embedding_and_cache: q / k / v mismatch");
+  TORCH_CHECK(query.stride(-1) == 1 && key.stride(-1) == 1 && value.stride(-1) == 1,
+              "rotary_embedding_and_cache: rows must be contiguous");
+  check(b200_rotary_embedding_and_cache(
+      positions.data_ptr<int64_t>(), query.data_ptr(), key.data_ptr(), value.data_ptr(), cos_sin_cache.data_ptr(),
+      key_cache.data_ptr(), value_cache.data_ptr(), slot_mapping.data_ptr<int64_t>(), (int)num_tokens,
+      (int)(query.size(-1) / head_size), (int)(key.size(-1) / head_size), (int)head_size, (int)cos_sin_cache.size(1),
+      query.stride(-2), key.stride(-2), value.stride(-2), is_neox ? 1 : 0, (int)key_cache.size(3),
+      (int)key_cache.size(4), dtype_code(query, "rotary_embedding_and_cache"), kv_code(kv_cache_dtype), (float)k_scale,
+      (float)v_scale, cur_stream()));
 }
 int64_t tp_flag_bytes() { return b200_tp_flag_bytes(); }
 
@@ -773,9 +793,14 @@ TORCH_LIBRARY(_C_custom_ar, custom_ar) {
 TORCH_LIBRARY(_C_b200, ext) {
   ext.def(
       "tp_allreduce_rows(int mc_base, Tensor block, int[] peer_bases, Tensor x, Tensor! out, "
-      "Tensor!? residual, Tensor? weight, float epsilon, int flag_off, int rank, int world) -> ()");
+      "Tensor!? residual, Tensor? weight, float epsilon, int flag_off, int rank, int world, int algo) -> ()");
   ext.impl("tp_allreduce_rows", torch::kCUDA, &tp_allreduce_rows);
   ext.def("tp_flag_bytes", &tp_flag_bytes);
+  ext.def(
+      "rotary_embedding_and_cache(Tensor positions, Tensor! query, Tensor! key, Tensor value, int head_size, "
+      "Tensor cos_sin_cache, bool is_neox, Tensor! key_cache, Tensor! value_cache, Tensor slot_mapping, "
+      "str kv_cache_dtype, float k_scale, float v_scale) -> ()");
+  ext.impl("rotary_embedding_and_cache", torch::kCUDA, &rotary_embedding_and_cache);
 }
 
 // `import <pkg>._C` support (kernels/core/registration.h:22-27 of the reference does the same)

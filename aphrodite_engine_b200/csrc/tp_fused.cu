@@ -14,6 +14,18 @@
 //                               multimem.st(H, out)                    NVSwitch replicates the row into every rank's H
 //   end barrier    (all rows of H have landed everywhere; nobody still reads X)
 //
+// Three algorithms (argument `algo`), same barriers, same row ownership:
+//   B200_TP_P2P        unicast everything: N peer loads summed in fp32 in rank order, N peer stores, N flag adds.
+//   B200_TP_MC_STORE   (default on NVSwitch) unicast loads + fp32 rank-order sum — BIT-IDENTICAL to the reference kernel's
+//                      arithmetic — and the switch used for what has no arithmetic in it: multimem.st replicates the
+//                      result (1 store instead of N) and multimem.red signals all peers with one instruction.
+//   B200_TP_MC_REDUCE  multimem.ld_reduce does the sum inside the switch (1 load instead of N). Measured on the B200
+//                      box: the switch does NOT round the fp32 sum to nearest-even when it narrows to bf16/f16
+//                      (tools/debug_tp_fused.py prints the census), so results differ from the reference's by up to an
+//                      ulp per reduction, with a bias; opt-in only.
+// With the row work laid out exactly like rms_norm_vec_kernel (256 threads, same vector-to-thread map, same reduction
+// tree) the P2P and MC_STORE variants reproduce all-reduce + fused_add_rms_norm BIT-EXACTLY, not just within tolerance.
+//
 // so the residual stream is touched by ONE rank per row (rank r keeps rows [r*ceil(T/N), ...) of `residual`, the other
 // rows of its buffer are never read), NVLink carries 2 x T*H*2 bytes per GPU per call (the algorithmic minimum of an
 // all-reduce), and the two flag barriers are one `multimem.red` each (a single instruction signals all peers; every rank
@@ -29,7 +41,7 @@
 
 namespace b200 {
 
-static constexpr int kTpThreads = 512;
+static constexpr int kTpThreads = 256;   // as rms_norm_vec_kernel: the row reduction must add in the same order
 static constexpr int kTpMaxBlocks = 128;   // flag slots per direction
 static constexpr int kTpMaxRanks = 8;
 
@@ -51,22 +63,40 @@ __device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
   return v;
 }
 
-template <bool MC>
+__device__ __forceinline__ uint32_t ld_relaxed_sys_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// RELEASE = false: the start barrier. Nothing written by this kernel has to be published (the partial sums were
+// written by the previous kernel on the stream and are visible at kernel start), so the signal is a relaxed add.
+// RELEASE = true: the end barrier. The signalling thread's release-add follows a CTA barrier, so by cumulativity it
+// publishes every thread's multimem.st / peer stores of this CTA — no per-thread system fence (65k MEMBAR.SYS cost
+// more than the whole exchange: measured 25 us -> see profiles/).
+enum { TP_P2P = 0, TP_MC_STORE = 1, TP_MC_REDUCE = 2 };
+
+template <int ALGO, bool RELEASE>
 __device__ __forceinline__ void tp_signal(const TpParams& p, int slot) {
   const int64_t off = p.flag_off + (int64_t)slot * 4;
-  if (MC) {
-    if (threadIdx.x == 0)
-      asm volatile("multimem.red.release.sys.global.add.u32 [%0], 1;" ::"l"(p.mc_base + off) : "memory");
+  if (ALGO != TP_P2P) {
+    if (threadIdx.x == 0) {
+      if (RELEASE) asm volatile("multimem.red.release.sys.global.add.u32 [%0], 1;" ::"l"(p.mc_base + off) : "memory");
+      else asm volatile("multimem.red.relaxed.sys.global.add.u32 [%0], 1;" ::"l"(p.mc_base + off) : "memory");
+    }
   } else {
-    if ((int)threadIdx.x < p.world)
-      asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(p.peer_base[threadIdx.x] + off) : "memory");
+    if ((int)threadIdx.x < p.world) {
+      if (RELEASE) asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(p.peer_base[threadIdx.x] + off) : "memory");
+      else asm volatile("red.relaxed.sys.global.add.u32 [%0], 1;" ::"l"(p.peer_base[threadIdx.x] + off) : "memory");
+    }
   }
 }
 __device__ __forceinline__ void tp_wait(const TpParams& p, int slot, uint32_t target) {
   if (threadIdx.x == 0) {
     const uint32_t* f = reinterpret_cast<const uint32_t*>(p.local_base + p.flag_off) + slot;
-    while ((int32_t)(ld_acquire_sys_u32(f) - target) < 0) {
+    while ((int32_t)(ld_relaxed_sys_u32(f) - target) < 0) {
     }
+    asm volatile("fence.acquire.sys;" ::: "memory");     // one acquire after the spin instead of one per poll
   }
   __syncthreads();
 }
@@ -106,9 +136,9 @@ __device__ __forceinline__ uint4 ld_peer_v4(const void* a) {
   return v;
 }
 
-template <typename T, bool MC>
+template <typename T, int ALGO>
 __device__ __forceinline__ uint4 tp_reduce_packet(const TpParams& p, int64_t byte_off) {
-  if constexpr (MC) {
+  if constexpr (ALGO == TP_MC_REDUCE) {
     return mc_ld_reduce<T>(p.mc_base + p.in_off + byte_off);
   } else {
   float acc[Pk<T>::N];
@@ -130,9 +160,9 @@ __device__ __forceinline__ uint4 tp_reduce_packet(const TpParams& p, int64_t byt
   return o.raw;
   }
 }
-template <bool MC>
+template <int ALGO>
 __device__ __forceinline__ void tp_broadcast_packet(const TpParams& p, int64_t byte_off, uint4 v) {
-  if (MC) {
+  if (ALGO != TP_P2P) {
     mc_st(p.mc_base + p.out_off + byte_off, v);
   } else {
 #pragma unroll
@@ -145,8 +175,8 @@ __device__ __forceinline__ void tp_broadcast_packet(const TpParams& p, int64_t b
 }
 
 // grid = min(rows per rank, kTpMaxBlocks) CTAs (identical on every rank); CTA b owns rows b, b+grid, ... of the slice.
-template <typename T, bool MC, bool NORM, int VPT>
-__global__ void __launch_bounds__(kTpThreads, 1) tp_allreduce_rows_kernel(const TpParams p) {
+template <typename T, int ALGO, bool NORM, int VPT>
+__global__ void __launch_bounds__(kTpThreads) tp_allreduce_rows_kernel(const TpParams p) {
   __shared__ float red[kTpThreads / 32];
   constexpr int N = Pk<T>::N;
   uint32_t* flags = reinterpret_cast<uint32_t*>(p.local_base + p.flag_off);
@@ -154,7 +184,7 @@ __global__ void __launch_bounds__(kTpThreads, 1) tp_allreduce_rows_kernel(const 
   const uint32_t t_start = (2u * epoch + 1u) * (uint32_t)p.world;
   const uint32_t t_end = (2u * epoch + 2u) * (uint32_t)p.world;
 
-  tp_signal<MC>(p, blockIdx.x);
+  tp_signal<ALGO, false>(p, blockIdx.x);
   tp_wait(p, blockIdx.x, t_start);
 
   const int rows_per = (p.num_tokens + p.world - 1) / p.world;
@@ -167,7 +197,7 @@ __global__ void __launch_bounds__(kTpThreads, 1) tp_allreduce_rows_kernel(const 
 #pragma unroll
     for (int k = 0; k < VPT; ++k) {
       const int v = threadIdx.x + k * kTpThreads;
-      if (v < nvec) z[k].raw = tp_reduce_packet<T, MC>(p, row * row_bytes + (int64_t)v * 16);
+      if (v < nvec) z[k].raw = tp_reduce_packet<T, ALGO>(p, row * row_bytes + (int64_t)v * 16);
     }
     if (NORM) {
       float ss = 0.f;
@@ -187,12 +217,12 @@ __global__ void __launch_bounds__(kTpThreads, 1) tp_allreduce_rows_kernel(const 
           *reinterpret_cast<uint4*>(res + (int64_t)v * N) = z[k].raw;
         }
       }
+      // the reduction tree of rms_norm_vec_kernel (block_sum_256): xor-shuffle warp sums, then the 8 warp sums in order
       ss = warp_sum(ss);
       __syncthreads();                       // `red` reuse across rows
       if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
       __syncthreads();
       float tot = 0.f;
-#pragma unroll
       for (int i = 0; i < kTpThreads / 32; ++i) tot += red[i];
       const float s = rsqrtf(tot / (float)p.hidden + p.eps);
 #pragma unroll
@@ -211,28 +241,26 @@ __global__ void __launch_bounds__(kTpThreads, 1) tp_allreduce_rows_kernel(const 
 #pragma unroll
     for (int k = 0; k < VPT; ++k) {
       const int v = threadIdx.x + k * kTpThreads;
-      if (v < nvec) tp_broadcast_packet<MC>(p, row * row_bytes + (int64_t)v * 16, z[k].raw);
+      if (v < nvec) tp_broadcast_packet<ALGO>(p, row * row_bytes + (int64_t)v * 16, z[k].raw);
     }
   }
-  // every thread's stores are ordered before the release-add of the signalling thread(s)
-  __threadfence_system();
-  __syncthreads();
-  tp_signal<MC>(p, blockIdx.x);
+  __syncthreads();                 // every thread's stores happen-before the release-add of the signalling thread(s)
+  tp_signal<ALGO, true>(p, blockIdx.x);
   tp_wait(p, blockIdx.x, t_end);
   if (threadIdx.x == 0) flags[kTpMaxBlocks + blockIdx.x] = epoch + 1u;
 }
 
-template <typename T, bool MC, bool NORM>
+template <typename T, int ALGO, bool NORM>
 static int launch_tp(const TpParams& p, cudaStream_t st) {
   const int nvec = p.hidden / Pk<T>::N;
   const int rows_per = (p.num_tokens + p.world - 1) / p.world;
   const int grid = std::max(1, std::min(rows_per, kTpMaxBlocks));
   if (nvec <= kTpThreads)
-    tp_allreduce_rows_kernel<T, MC, NORM, 1><<<grid, kTpThreads, 0, st>>>(p);
+    tp_allreduce_rows_kernel<T, ALGO, NORM, 1><<<grid, kTpThreads, 0, st>>>(p);
   else if (nvec <= 2 * kTpThreads)
-    tp_allreduce_rows_kernel<T, MC, NORM, 2><<<grid, kTpThreads, 0, st>>>(p);
+    tp_allreduce_rows_kernel<T, ALGO, NORM, 2><<<grid, kTpThreads, 0, st>>>(p);
   else
-    tp_allreduce_rows_kernel<T, MC, NORM, 4><<<grid, kTpThreads, 0, st>>>(p);
+    tp_allreduce_rows_kernel<T, ALGO, NORM, 4><<<grid, kTpThreads, 0, st>>>(p);
   return check_launch("tp_allreduce_rows_kernel");
 }
 
@@ -245,12 +273,14 @@ extern "C" int64_t b200_tp_flag_bytes(void) { return (int64_t)(2 * kTpMaxBlocks 
 extern "C" int b200_tp_allreduce_rows(void* mc_base, void* local_base, const int64_t* peer_bases, int64_t in_off,
                                       int64_t out_off, int64_t flag_off, void* residual, const void* weight,
                                       float epsilon, int num_tokens, int hidden, int rank, int world, int dtype,
-                                      void* stream) {
+                                      int algo, void* stream) {
   B200_CHECK(dtype == B200_F16 || dtype == B200_BF16, "tp_allreduce_rows: float16 / bfloat16 only");
   B200_CHECK(world >= 2 && world <= kTpMaxRanks && rank >= 0 && rank < world, "tp_allreduce_rows: bad rank / world");
-  B200_CHECK(local_base != nullptr && (mc_base != nullptr || peer_bases != nullptr),
-             "tp_allreduce_rows: needs a multicast mapping or the peer table");
-  B200_CHECK(hidden % 8 == 0 && hidden / 8 <= 4 * kTpThreads, "tp_allreduce_rows: hidden must be a multiple of 8, <= 16384");
+  B200_CHECK(algo >= TP_P2P && algo <= TP_MC_REDUCE, "tp_allreduce_rows: algo must be 0 (p2p), 1 (multicast store) or 2 (multicast reduce)");
+  B200_CHECK(local_base != nullptr, "tp_allreduce_rows: no symmetric block");
+  B200_CHECK(algo == TP_P2P || mc_base != nullptr, "tp_allreduce_rows: this algorithm needs the multicast mapping");
+  B200_CHECK(algo == TP_MC_REDUCE || peer_bases != nullptr, "tp_allreduce_rows: this algorithm needs the peer table");
+  B200_CHECK(hidden % 8 == 0 && hidden / 8 <= 4 * kTpThreads, "tp_allreduce_rows: hidden must be a multiple of 8, <= 8192");
   B200_CHECK(((in_off | out_off) & 15) == 0 && (flag_off & 127) == 0, "tp_allreduce_rows: misaligned offsets");
   B200_CHECK((residual == nullptr) == (weight == nullptr), "tp_allreduce_rows: residual and weight go together");
   B200_CHECK(((reinterpret_cast<uintptr_t>(residual) | reinterpret_cast<uintptr_t>(weight)) & 15) == 0,
@@ -267,10 +297,10 @@ extern "C" int b200_tp_allreduce_rows(void* mc_base, void* local_base, const int
   p.residual = residual; p.weight = weight; p.eps = epsilon;
   p.num_tokens = num_tokens; p.hidden = hidden; p.rank = rank; p.world = world;
   cudaStream_t st = (cudaStream_t)stream;
-  const bool mc = mc_base != nullptr, norm = residual != nullptr;
-#define B200_TP(T)                                                               \
-  (mc ? (norm ? launch_tp<T, true, true>(p, st) : launch_tp<T, true, false>(p, st)) \
-      : (norm ? launch_tp<T, false, true>(p, st) : launch_tp<T, false, false>(p, st)))
+  const bool norm = residual != nullptr;
+#define B200_TP_A(T, A) (norm ? launch_tp<T, A, true>(p, st) : launch_tp<T, A, false>(p, st))
+#define B200_TP(T) (algo == TP_P2P ? B200_TP_A(T, TP_P2P) : (algo == TP_MC_STORE ? B200_TP_A(T, TP_MC_STORE) : B200_TP_A(T, TP_MC_REDUCE)))
   return dtype == B200_BF16 ? B200_TP(__nv_bfloat16) : B200_TP(__half);
 #undef B200_TP
+#undef B200_TP_A
 }

@@ -21,6 +21,12 @@ import torch.distributed as dist
 from .. import _native
 
 
+# Symmetric allocations are process-lifetime objects: peers hold mappings of them and CUDA graphs bake their addresses
+# in, and torch's allocator synchronises the device inside the tensor destructor (observed: std::terminate when a block
+# was released while the process group was still alive). They are therefore never freed.
+_KEEPALIVE = []
+
+
 def _ops():
     _native.load_torch_ops()
     return torch.ops._C_b200
@@ -29,8 +35,13 @@ def _ops():
 class NvlsTensorParallel:
     """One instance per (process group, max_tokens, hidden, dtype). Every rank must issue the same call sequence."""
 
+    ALGOS = {"p2p": 0, "mc_store": 1, "mc_reduce": 2}       # B200_TP_* of include/b200_decode.h
+
     def __init__(self, group: dist.ProcessGroup, device: torch.device, max_tokens: int, hidden: int,
-                 dtype: torch.dtype = torch.bfloat16, use_multicast: bool = True) -> None:
+                 dtype: torch.dtype = torch.bfloat16, algo: str = "auto") -> None:
+        """algo: "p2p" (unicast peer pointers only), "mc_store" (unicast fp32 rank-order reduce — bit-identical to the
+        reference's all-reduce — + multicast store and flags), "mc_reduce" (the switch reduces; not bit-identical),
+        "auto" = "mc_store" when the fabric gives a multicast mapping, else "p2p"."""
         import torch.distributed._symmetric_memory as symm_mem
         assert dtype in (torch.bfloat16, torch.float16), "fused TP exchange: float16 / bfloat16"
         assert hidden % 8 == 0
@@ -45,12 +56,20 @@ class NvlsTensorParallel:
         self.block = symm_mem.empty(nbytes, dtype=torch.uint8, device=self.device)
         hdl = symm_mem.rendezvous(self.block, group.group_name)
         self._hdl = hdl
+        _KEEPALIVE.append((self.block, hdl))
         off = int(getattr(hdl, "offset", 0))
         self.peer_bases = [int(p) + off for p in hdl.buffer_ptrs]
         assert self.peer_bases[self.rank] == self.block.data_ptr(), "symmetric block is not at its advertised address"
         mc = int(hdl.multicast_ptr)
-        self.mc_base = (mc + off) if (use_multicast and mc != 0) else 0
-        self.multicast = self.mc_base != 0
+        self.has_multicast = mc != 0
+        if algo == "auto":
+            algo = "mc_store" if self.has_multicast else "p2p"
+        assert algo in self.ALGOS, algo
+        if algo != "p2p" and not self.has_multicast:
+            raise RuntimeError(f"NvlsTensorParallel: algo {algo!r} needs a multicast mapping, this box has none")
+        self.algo = algo
+        self.mc_base = (mc + off) if self.has_multicast else 0
+        self.multicast = algo != "p2p"
         # barrier counters start at zero on every rank before anybody signals
         self.block.zero_()
         torch.cuda.synchronize(self.device)
@@ -75,7 +94,7 @@ class NvlsTensorParallel:
     # ---- the exchange ------------------------------------------------------------------------------------------
     def _launch(self, num_tokens: int, residual: Optional[torch.Tensor], weight: Optional[torch.Tensor], eps: float):
         _ops().tp_allreduce_rows(self.mc_base, self.block, self.peer_bases, self.x(num_tokens), self.h(num_tokens),
-                                 residual, weight, eps, 0, self.rank, self.world)
+                                 residual, weight, eps, 0, self.rank, self.world, self.ALGOS[self.algo])
         return self.h(num_tokens)
 
     def allreduce_add_rms_norm(self, num_tokens: int, residual: torch.Tensor, weight: torch.Tensor,

@@ -32,6 +32,7 @@ import torch
 import torch.nn.functional as F
 
 from . import _custom_ops as ops
+from . import ext_ops
 from .attention.paged_attn import PagedAttention
 
 
@@ -72,7 +73,8 @@ class LlamaDecoder:
                  device, dtype=torch.bfloat16, kv_cache_dtype: str = "auto", tp_rank: int = 0,
                  tp_size: int = 1, group=None, seed: int = 1234, layers: Optional[int] = None,
                  kv_fill: bool = True, quant: Optional[str] = None, group_size: int = 128,
-                 custom_ar=None, nvls=None, op_table=None, attention_cls=None, share_from: "LlamaDecoder" = None):
+                 custom_ar=None, nvls=None, op_table=None, attention_cls=None, share_from: "LlamaDecoder" = None,
+                 fuse_rope_cache: Optional[bool] = None):
         assert shape.heads % tp_size == 0 and shape.kv_heads % tp_size == 0
         assert shape.intermediate % tp_size == 0 and shape.vocab % tp_size == 0
         self.s, self.batch, self.block_size = shape, batch, block_size
@@ -85,6 +87,8 @@ class LlamaDecoder:
         # the op table (this package's kernels unless a checker substitutes the reference's) and its attention glue
         self.ops = ops if op_table is None else op_table
         self.attn = PagedAttention if attention_cls is None else attention_cls
+        # rotary + cache write as one launch (ext_ops; same outputs) unless a substituted op table is being timed
+        self.fuse_rope_cache = (op_table is None) if fuse_rope_cache is None else fuse_rope_cache
         self.n_layers = shape.layers if layers is None else layers
         self.heads = shape.heads // tp_size
         self.kv_heads = shape.kv_heads // tp_size
@@ -108,7 +112,8 @@ class LlamaDecoder:
         else:
             self._init_weights(seed, group_size)
             self._init_kv_cache(num_blocks, kv_fill, seed)
-        per_layer = 6 + (4 if quant == "gptq" else 0)       # norm x2, rope, cache write, attention, act (+ 4 W4A16 GEMMs)
+        # norm x2 (or 2 fused exchanges), rope, cache write (one launch when fused), attention, act (+ 4 W4A16 GEMMs)
+        per_layer = 6 - (1 if self.fuse_rope_cache else 0) + (4 if quant == "gptq" else 0)
         if self.tp_mode == "p2p":
             per_layer += 2
         self.my_kernel_launches_per_step = per_layer * self.n_layers + 1
@@ -265,11 +270,15 @@ class LlamaDecoder:
         for li, L in enumerate(self.layers):
             qkv = self._linear(hidden, L["qkv"])
             q, k, v = qkv.split([self.q_size, self.kv_size, self.kv_size], dim=-1)
-            o.rotary_embedding(st.positions, q, k, s.head_size, self.cos_sin, True)
             kc, vc = self.kv_views[li]
-            self.attn.write_to_paged_cache(k.view(-1, self.kv_heads, s.head_size),
-                                           v.view(-1, self.kv_heads, s.head_size), kc, vc,
-                                           st.slot_mapping, self.kv_cache_dtype, 1.0, 1.0)
+            if self.fuse_rope_cache:
+                ext_ops.rotary_embedding_and_cache(st.positions, q, k, v, s.head_size, self.cos_sin, True, kc, vc,
+                                                   st.slot_mapping, self.kv_cache_dtype, 1.0, 1.0)
+            else:
+                o.rotary_embedding(st.positions, q, k, s.head_size, self.cos_sin, True)
+                self.attn.write_to_paged_cache(k.view(-1, self.kv_heads, s.head_size),
+                                               v.view(-1, self.kv_heads, s.head_size), kc, vc,
+                                               st.slot_mapping, self.kv_cache_dtype, 1.0, 1.0)
             qv = q.view(-1, self.heads, s.head_size)
             attn_out = torch.empty(self.batch, self.heads, s.head_size, dtype=self.dtype,
                                    device=self.device)

@@ -66,10 +66,12 @@ def parse():
     ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--cpu-sample-layers", type=int, default=2)
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--allreduce", default="auto", choices=["auto", "nvls", "nvls-p2p", "p2p", "nccl"],
-                    help="TP exchange: nvls = fused NVSwitch-multicast reduce+norm kernel; nvls-p2p = the same kernel over "
+    ap.add_argument("--allreduce", default="auto", choices=["auto", "nvls", "nvls-reduce", "nvls-p2p", "p2p", "nccl"],
+                    help="TP exchange: nvls = fused exchange kernel (fp32 rank-order reduce over peer loads, multicast store "
+                         "+ flags: bit-identical to the reference's all-reduce + norm); nvls-reduce = the switch sums "
+                         "(multimem.ld_reduce; not round-to-nearest, tolerance only); nvls-p2p = the fused kernel over "
                          "unicast peer pointers; p2p = IPC peer-memory all-reduce kernel + norm; nccl; auto = the first of "
-                         "these that is available AND passes the in-run exact parity check")
+                         "nvls / nvls-p2p / p2p / nccl that is available AND passes the in-run exact parity check")
     ap.add_argument("--quant", default=None, choices=[None, "gptq"],
                     help="gptq = BASELINE configs[2] (GPTQ int4 Marlin W4A16 linears); default bf16 = configs[1]")
     return ap.parse_args()
@@ -352,7 +354,7 @@ def exchange_parity_exact(env, mode, nvls, ca, batch, hidden, dtype):
         dist.all_reduce(ref_h)
         ref_res = res0.clone()
         ops.fused_add_rms_norm(ref_h, ref_res, w, 1e-5)
-        if mode in ("nvls", "nvls-p2p"):
+        if nvls is not None:
             nvls.x(batch).copy_(x)
             res = res0.clone()
             h = nvls.allreduce_add_rms_norm(batch, res, w, 1e-5)
@@ -372,8 +374,8 @@ def setup_exchange(env, args, hidden, dtype):
     """Chooses the TP exchange implementation. Returns (mode, nvls, ca, parity_report)."""
     if env.world == 1:
         return "none", None, None, None
-    order = {"auto": ["nvls", "nvls-p2p", "p2p", "nccl"], "nvls": ["nvls"], "nvls-p2p": ["nvls-p2p"], "p2p": ["p2p"],
-             "nccl": ["nccl"]}[args.allreduce]
+    order = {"auto": ["nvls", "nvls-p2p", "p2p", "nccl"]}.get(args.allreduce, [args.allreduce])
+    nvls_algo = {"nvls": "mc_store", "nvls-reduce": "mc_reduce", "nvls-p2p": "p2p"}
     report = {}
     for mode in order:
         if mode == "nccl":
@@ -382,11 +384,9 @@ def setup_exchange(env, args, hidden, dtype):
         nvls = ca = None
         why = None
         try:
-            if mode in ("nvls", "nvls-p2p"):
+            if mode in nvls_algo:
                 from aphrodite_engine_b200.distributed.nvls import NvlsTensorParallel
-                nvls = NvlsTensorParallel(env.group, env.dev, args.batch, hidden, dtype, use_multicast=(mode == "nvls"))
-                if mode == "nvls" and not nvls.multicast:
-                    why = "no multicast mapping on this box"
+                nvls = NvlsTensorParallel(env.group, env.dev, args.batch, hidden, dtype, algo=nvls_algo[mode])
             else:
                 from aphrodite_engine_b200.distributed import CustomAllreduce
                 ca = CustomAllreduce(env.cpu_group, env.dev)
@@ -580,7 +580,8 @@ def run_b200(args):
         "config": {"workload": f"Llama-3-8B bf16 paged-attention decode bs={args.batch} ctx={args.ctx} "
                                f"block={args.block_size} layers={shape.layers} "
                                + ("GPTQ int4 Marlin W4A16 linears (BASELINE configs[2])" if args.quant else "(BASELINE configs[1])"),
-                   "parallelism": f"tp{world}", "allreduce": {"none": "none", "nvls": "nvls-fused (multimem reduce + add + rms_norm)",
+                   "parallelism": f"tp{world}", "allreduce": {"none": "none", "nvls": "nvls-fused (peer-load fp32 reduce + add + rms_norm + multimem store)",
+                                                              "nvls-reduce": "nvls-fused (multimem.ld_reduce + add + rms_norm + multimem store)",
                                                               "nvls-p2p": "fused kernel over unicast peer pointers",
                                                               "p2p": "nvlink-p2p", "nccl": "nccl"}[mode],
                    "kv_cache_dtype": args.kv_cache_dtype,

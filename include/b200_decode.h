@@ -141,6 +141,17 @@ int b200_rotary_embedding(const int64_t* positions, void* query, void* key,
                           int num_tokens, int num_heads, int num_kv_heads, int head_size,
                           int rot_dim, int64_t query_stride, int64_t key_stride,
                           int is_neox, int dtype, void* stream);
+/* rotary_embedding followed by reshape_and_cache as one launch (extension; torch op _C_b200::rotary_embedding_and_cache).
+ * Outputs are those of b200_rotary_embedding(query, key) then b200_reshape_and_cache(key, value, ...) — bit-exact:
+ * q and k rotated in place, rotated k and v written to the paged cache at slot_mapping[t] (negative = skip the write).
+ * The fused kernel serves NeoX style, rot_dim == head_size, f16/bf16, 16-byte aligned rows; anything else runs the two
+ * kernels back to back inside this call. */
+int b200_rotary_embedding_and_cache(const int64_t* positions, void* query, void* key, const void* value,
+                                    const void* cos_sin_cache, void* key_cache, void* value_cache,
+                                    const int64_t* slot_mapping, int num_tokens, int num_heads, int num_kv_heads,
+                                    int head_size, int rot_dim, int64_t query_stride, int64_t key_stride,
+                                    int64_t value_stride, int is_neox, int block_size, int x, int dtype,
+                                    int kv_dtype, float k_scale, float v_scale, void* stream);
 /* act: 0 silu_and_mul, 1 gelu_and_mul, 2 gelu_tanh_and_mul  (input [T, 2d] -> out [T, d]) */
 int b200_act_and_mul(void* out, const void* input, int num_tokens, int d, int act,
                      int dtype, void* stream);
@@ -168,6 +179,11 @@ int b200_activation(void* out, const void* input, int num_tokens, int d, int act
  * partition ignores split_k. Act-order with the full k range is handled by the caller
  * permuting A's columns (b200_permute_cols), as the reference does with a_tmp (gptq_marlin.cu:2145-2158). */
 int b200_marlin_gemm_plan(int size_m, int size_n, int size_k, int num_groups);
+/* The dense launch's work plan for a shape (size_m > 32): out5 = {whole tiles, tail CTAs, 64-k chunks per k-unit,
+ * k-units per tile, max CTAs sharing one tile}. Whole tiles fill complete waves of the SMs; the tiles of the last
+ * partial wave are shared by `tail CTAs` in equal contiguous (tile, k-unit) ranges, each shared tile reduced through
+ * fp32 slabs by the last CTA to arrive on the tile's lock (segment order, deterministic). Host arithmetic only. */
+int b200_marlin_dense_plan(int size_m, int size_n, int size_k, int num_groups, int* out5);
 /* debug only: per-role cycle attribution of the last GEMM launched with B200_MARLIN_DEBUG & 16 (32 x u64) */
 int b200_debug_marlin_prof(unsigned long long* out32);
 int b200_gptq_marlin_gemm(const void* a, const void* b_q_weight, const void* b_scales,
@@ -237,7 +253,7 @@ int b200_car_register_graph_buffers(int64_t fa, const void* handles, const int64
  *          -> fused_add_rms_norm (kernels/layernorm_kernels.cu:204-286, aphrodite/modeling/models/llama.py:250-256)
  * with one kernel. Every rank owns one SYMMETRIC allocation (same layout on all ranks) that is mapped on every peer
  * (`peer_bases[world]`, unicast VAs as int64; peer_bases[rank] == local_base) and, when the fabric supports it, bound
- * to one multicast object mapped at `mc_base` (NULL: the unicast peer-pointer variant of the same algorithm runs).
+ * to one multicast object mapped at `mc_base` (NULL when the fabric has none: only B200_TP_P2P is available).
  * Inside the allocation, at byte offsets: `in_off` the rank's partial sums X [num_tokens, hidden] (the row-parallel
  * GEMM's output), `out_off` the result H [num_tokens, hidden] (identical on all ranks afterwards), `flag_off`
  * b200_tp_flag_bytes() bytes of barrier state, ZERO before the first call (and a host barrier after zeroing).
@@ -245,13 +261,18 @@ int b200_car_register_graph_buffers(int64_t fa, const void* handles, const int64
  * residual <- sum + residual for THIS RANK'S rows only, rows [rank*ceil(T/world), ...) — the residual stream is
  * token-sharded across ranks (each row is owned by one rank for the whole forward pass).
  * residual == weight == NULL: H = sum_r X_r (plain all-reduce, fp32 accumulate, one rounding).
- * fp16 / bf16, hidden % 8 == 0, hidden <= 16384. Stream-ordered, no host state: CUDA-graph capturable. Every rank
- * must issue the same sequence of calls (the barriers pair launches by order). */
+ * fp16 / bf16, hidden % 8 == 0, hidden <= 8192. Stream-ordered, no host state: CUDA-graph capturable. Every rank
+ * must issue the same sequence of calls (the barriers pair launches by order).
+ * algo: B200_TP_P2P (unicast loads / stores / flags: needs only peer_bases), B200_TP_MC_STORE (unicast loads summed
+ * in fp32 in rank order — the reference kernel's arithmetic, bit for bit — then multimem.st / multimem.red through the
+ * switch: needs both mappings), B200_TP_MC_REDUCE (multimem.ld_reduce: the switch sums; its narrowing to 16 bits is
+ * not round-to-nearest-even, so results are NOT bit-identical to the reference: opt-in). */
+enum { B200_TP_P2P = 0, B200_TP_MC_STORE = 1, B200_TP_MC_REDUCE = 2 };
 int64_t b200_tp_flag_bytes(void);
 int b200_tp_allreduce_rows(void* mc_base, void* local_base, const int64_t* peer_bases, int64_t in_off,
                            int64_t out_off, int64_t flag_off, void* residual, const void* weight,
                            float epsilon, int num_tokens, int hidden, int rank, int world, int dtype,
-                           void* stream);
+                           int algo, void* stream);
 
 /* ---- small adjacent ops ------------------------------------------------------------------------------
  * replaces permute_cols            kernels/permute_cols.cu (schema torch_bindings.cpp:218-219): out[m,k] = a[m,perm[k]]

@@ -1,9 +1,13 @@
 """Multi-GPU parity (>= 2 GPUs): the fused NVSwitch exchange kernel (csrc/tp_fused.cu) against the sequence it replaces —
-NCCL all-reduce followed by this package's `fused_add_rms_norm` (itself pinned to the reference kernel in
-test_gpu_vs_ref_cuda.py). Small integers make every partial sum exact in bf16/fp16 (the trick of the reference's
-tests/distributed/test_custom_all_reduce.py:55-81), so the comparison is `torch.equal`; a second pass with random
-normal inputs checks the fp32-accumulate / single-rounding numerics within 1 bf16 ulp of an fp32 restatement.
-Both the multicast (multimem) and the unicast peer-pointer variants run, eagerly and under CUDA-graph replay."""
+a sum all-reduce followed by this package's `fused_add_rms_norm` (itself pinned to the reference kernel in
+test_gpu_vs_ref_cuda.py).
+  * small integers: every partial sum is exact in bf16/fp16 (the trick of the reference's
+    tests/distributed/test_custom_all_reduce.py:55-81), so all three algorithms must equal NCCL + norm bit for bit;
+  * random normal inputs: the reference's custom all-reduce accumulates in fp32 in rank order and rounds once
+    (kernels/all_reduce/custom_all_reduce.cuh:150-168); "p2p" and "mc_store" restate exactly that, so they must equal
+    [gather the ranks' inputs -> fp32 rank-order sum -> round -> fused_add_rms_norm] BIT FOR BIT at any world size;
+    "mc_reduce" (the switch sums, and does not round to nearest) is only held to a 2-ulp tolerance.
+Eagerly and under CUDA-graph replay (two chained exchanges, as in a decoder layer)."""
 import os
 import socket
 
@@ -32,14 +36,26 @@ def _worker(rank, world, port, q):
         import aphrodite_engine_b200._custom_ops as ops
         from aphrodite_engine_b200.distributed.nvls import NvlsTensorParallel
         msgs, info = [], {}
+        def exact_sum(x):
+            """fp32 sum of the ranks' tensors in rank order, rounded once to x.dtype."""
+            parts = [torch.empty_like(x) for _ in range(world)]
+            dist.all_gather(parts, x)
+            acc = torch.zeros_like(x, dtype=torch.float32)
+            for part in parts:
+                acc += part.float()
+            return acc.to(x.dtype)
+
         for dtype in (torch.bfloat16, torch.float16):
-            for use_mc in (True, False):
+            for algo in ("mc_store", "mc_reduce", "p2p"):
                 H, TMAX = 4096, 300
-                tp = NvlsTensorParallel(dist.group.WORLD, dev, TMAX, H, dtype, use_multicast=use_mc)
-                info[f"multicast_{use_mc}"] = tp.multicast
-                if use_mc and not tp.multicast:
-                    msgs.append("note: no multicast mapping on this box; multimem variant not exercised")
-                tag = f"{dtype} mc={tp.multicast}"
+                try:
+                    tp = NvlsTensorParallel(dist.group.WORLD, dev, TMAX, H, dtype, algo=algo)
+                except RuntimeError as e:
+                    msgs.append(f"note: {algo} not exercised ({e})")
+                    continue
+                info[algo] = True
+                exact = algo != "mc_reduce"
+                tag = f"{dtype} {algo}"
                 w = (torch.randint(1, 4, (H,), device=dev)).to(dtype)
                 dist.broadcast(w, 0)
                 for T in (1, 7, 256, 300):
@@ -71,23 +87,25 @@ def _worker(rank, world, port, q):
                     torch.cuda.synchronize()
                     if not torch.equal(h2, ref_sum):
                         msgs.append(f"{tag} T={T}: plain all-reduce differs")
-                    # ---- numerics: random normal, fp32 restatement --------------------------------------------
+                    # ---- random normal inputs: fp32 rank-order sum, one rounding, then the norm kernel ------------
                     xr = torch.randn(T, H, device=dev).to(dtype)
                     rr = torch.randn(T, H, device=dev).to(dtype)
                     dist.broadcast(rr, 0)
-                    s32 = xr.float().clone()
-                    dist.all_reduce(s32)
-                    z = (s32.to(dtype).float() + rr.float()).to(dtype)
-                    var = z.float().pow(2).mean(-1, keepdim=True)
-                    want = ((z.float() * torch.rsqrt(var + 1e-5)).to(dtype).float() * w.float()).to(dtype)
+                    want_h, want_res = exact_sum(xr), rr.clone()
+                    ops.fused_add_rms_norm(want_h, want_res, w, 1e-5)
                     tp.x(T).copy_(xr)
                     res = rr.clone()
                     h = tp.allreduce_add_rms_norm(T, res, w, 1e-5)
                     torch.cuda.synchronize()
-                    err = (h.float() - want.float()).abs()
-                    tol = 2e-2 * want.float().abs() + 2e-2     # 1-2 ulp of a 16-bit type after a differently-ordered fp32 sum
-                    if not bool((err <= tol).all()):
-                        msgs.append(f"{tag} T={T}: random-normal mismatch max err {float(err.max())}")
+                    if exact:
+                        if not (torch.equal(h, want_h) and torch.equal(res[lo:hi], want_res[lo:hi])):
+                            msgs.append(f"{tag} T={T}: random-normal result not bit-identical to fp32 rank-order sum + norm "
+                                        f"(max {float((h.float() - want_h.float()).abs().max())})")
+                    else:
+                        err = (h.float() - want_h.float()).abs()
+                        tol = 2e-2 * want_h.float().abs() + 2e-2     # ~2 ulp of a 16-bit type
+                        if not bool((err <= tol).all()):
+                            msgs.append(f"{tag} T={T}: random-normal mismatch max err {float(err.max())}")
                 # ---- CUDA graph: two chained exchanges per replay, as in a decoder layer ---------------------------
                 T = 256
                 xin = torch.zeros(T, H, dtype=dtype, device=dev)
@@ -102,22 +120,24 @@ def _worker(rank, world, port, q):
                     out = h2.clone()
                 for it in range(4):
                     torch.manual_seed(77 * it + rank)
-                    xin.copy_(torch.randint(-2, 3, (T, H), device=dev).to(dtype))
-                    r0 = torch.randint(-2, 3, (T, H), device=dev).to(dtype)
+                    xin.copy_(torch.randn(T, H, device=dev).to(dtype))
+                    r0 = torch.randn(T, H, device=dev).to(dtype)
                     dist.broadcast(r0, 0)
                     res.copy_(r0)
                     g.replay()
                     torch.cuda.synchronize()
-                    a = xin.clone(); dist.all_reduce(a)
+                    a = exact_sum(xin)
                     rres = r0.clone()
                     ops.fused_add_rms_norm(a, rres, w, 1e-5)
-                    b = a.clone(); dist.all_reduce(b)
+                    b = exact_sum(a)
                     ops.fused_add_rms_norm(b, rres, w, 1e-5)
                     lo, hi = tp.rows_of(rank, T)
-                    if not (torch.equal(out, b) and torch.equal(res[lo:hi], rres[lo:hi])):
-                        msgs.append(f"{tag}: graph replay {it} differs (max {float((out.float()-b.float()).abs().max())})")
+                    if exact:
+                        if not (torch.equal(out, b) and torch.equal(res[lo:hi], rres[lo:hi])):
+                            msgs.append(f"{tag}: graph replay {it} differs (max {float((out.float()-b.float()).abs().max())})")
+                    elif not bool(((out.float() - b.float()).abs() <= 4e-2 * b.float().abs() + 4e-2).all()):
+                        msgs.append(f"{tag}: graph replay {it} outside tolerance")
                 dist.barrier(); torch.cuda.synchronize()
-                del tp
         ok = not [m for m in msgs if not m.startswith("note:")]
         q.put((rank, ok, msgs, info))
         dist.barrier()
@@ -129,7 +149,7 @@ def _worker(rank, world, port, q):
         os._exit(0)
 
 
-@pytest.mark.timeout(300)
+@pytest.mark.timeout(200)
 @pytest.mark.parametrize("world", [2, 4, 8])
 def test_tp_fused_exchange_matches_nccl_plus_norm(world):
     if torch.cuda.device_count() < world:
@@ -140,7 +160,7 @@ def test_tp_fused_exchange_matches_nccl_plus_norm(world):
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=240) for _ in range(world)]
+    res = [q.get(timeout=150) for _ in range(world)]
     for p in procs:
         p.join(timeout=30)
     for rank, ok, msgs, info in res:
