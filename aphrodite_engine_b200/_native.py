@@ -34,6 +34,7 @@ SIGNATURES = {
                                [c_float] * 2 + [c_int] * 5 + [c_void_p],
     "b200_set_attention_impl": [c_int],
     "b200_last_attention_path": [],
+    "b200_last_attention_cluster_split": [],
     "b200_reshape_and_cache": [c_void_p] * 5 + [c_int] * 5 + [c_int64] * 2 + [c_int] * 2 +
                               [c_float] * 2 + [c_void_p],
     "b200_reshape_and_cache_flash": [c_void_p] * 5 + [c_int] * 4 + [c_int64] * 3 + [c_int] * 2 +
@@ -49,7 +50,6 @@ SIGNATURES = {
     "b200_act_and_mul": [c_void_p] * 2 + [c_int] * 4 + [c_void_p],
     "b200_activation": [c_void_p] * 2 + [c_int] * 4 + [c_void_p],
     "b200_marlin_gemm_plan": [c_int] * 4,
-    "b200_marlin_dense_plan": [c_int] * 4 + [c_void_p],
     "b200_debug_marlin_prof": [c_void_p],
     "b200_gptq_marlin_gemm": [c_void_p] * 7 + [c_int] * 8 + [c_void_p],
     "b200_marlin_gemm_moe": [c_void_p] * 3 + [c_int64] + [c_void_p] * 7 + [c_int] * 10 + [c_void_p],
@@ -57,6 +57,7 @@ SIGNATURES = {
     "b200_awq_marlin_repack": [c_void_p] * 2 + [c_int] * 3 + [c_void_p],
     "b200_moe_align_block_size": [c_void_p, c_int, c_int64, c_int, c_int] + [c_void_p] * 4,
     "b200_topk_softmax": [c_void_p] * 4 + [c_int] * 3 + [c_void_p],
+    "b200_moe_expert_scale_add": [c_void_p] * 4 + [c_int] * 6 + [c_void_p],
     "b200_permute_cols": [c_void_p] * 3 + [c_int64, c_int, c_void_p],
     "b200_awq_dequantize": [c_void_p] * 4 + [c_int64, c_int, c_int, c_void_p],
     "b200_advance_step_flashattn": [c_int] * 3 + [c_void_p] * 6 + [c_int64, c_void_p],

@@ -32,9 +32,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
-#include <array>
 #include <type_traits>
-#include <vector>
 
 namespace b200 {
 
@@ -74,14 +72,8 @@ struct MarlinParams {
   int* locks;            // >= tiles ints, zero on entry, returned to zero (the reference's `workspace`)
   int M, N, K;
   int group_size;        // -1 = channel-wise (single scale row)
-  // dense launch: CTAs [0, full_tiles) take one whole tile each (full waves); the remaining `tail` tiles are cut
-  // stream-k style: their (tile, k-unit) pairs, tile-major, are divided into `tail_ctas` equal contiguous ranges
-  int full_tiles;
-  int tiles_x;           // 128-channel tiles along N (tile t -> (t % tiles_x, t / tiles_x))
-  int tail_ctas;         // CTAs sharing the tail tiles (0: no tail)
-  int unit_chunks;       // 64-k chunks per k-unit (= chunks per scale group, so ranges start on group boundaries)
-  int units_per_tile;    // K / 64 / unit_chunks
-  long long tail_units;  // tail tiles * units_per_tile
+  int chunks_per_split;  // 64-wide k chunks handled by one CTA
+  int split_k;
   int box_rows;          // rows of the activation TMA box (tokens rounded up to 16, <= 256)
   int grouped;           // 1: b_scales has one row per k-group (Marlin "grouped" permutation), 0: single row
   int rows_per_chunk;    // scale rows a 64-wide chunk spans (1, or 2 when group_size == 32)
@@ -205,16 +197,11 @@ marlin_w4a16_tc5_kernel(const __grid_constant__ CUtensorMap tmap_a, const Marlin
   uint32_t* turn = tmem_slot + 1;                   // next chunk whose MMAs may be issued (orders the two issuers)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // Dense launch: a 1-D list of CTAs. The first `full_tiles` (a multiple of the SM count) take one whole tile each;
-  // the tiles of the last, partial wave are shared stream-k style by `tail_ctas` CTAs: the (tile, k-unit) pairs of the
-  // tail, tile-major, are divided into equal contiguous ranges, so 224 tiles on 148 SMs cost 1 + 76/148 tile-times
-  // instead of 2. A range crosses at most a few tile boundaries; the CTA runs its (tile, k-range) SEGMENTS one after
-  // the other through the same pipeline (barriers re-armed in between, the TMEM accumulator reused). A tile covered by
-  // several CTAs is reduced through fp32 slabs by the last CTA to arrive (ticket), in segment order.
-  // Grouped launch: (n tile, (expert, row tile)), one segment.
+  const int n_base = blockIdx.x * MG_NT;
+  int tok_base = blockIdx.y * MG_TOK;                        // first row of this CTA in the TMA'd activation matrix
+  int toks = min(MG_TOK, p.M - tok_base);
   const uint32_t* b_q = p.b_q;
   const T* sc = reinterpret_cast<const T*>(p.scales);
-  int moe_tok_base = 0, moe_toks = 0;
   if constexpr (MOE) {
     // blockIdx.y -> (expert, tile of its sorted-row segment). Uniform over the CTA, so surplus CTAs of the
     // upper-bound grid leave before any barrier / TMEM allocation.
@@ -227,24 +214,18 @@ marlin_w4a16_tc5_kernel(const __grid_constant__ CUtensorMap tmap_a, const Marlin
       t -= nt;
     }
     if (e >= p.num_experts) return;
-    moe_tok_base = seg0 + t * p.tile_rows;
-    moe_toks = min(p.tile_rows, len - t * p.tile_rows);
+    tok_base = seg0 + t * p.tile_rows;
+    toks = min(p.tile_rows, len - t * p.tile_rows);
     b_q += (size_t)e * p.expert_words;
     sc += (size_t)e * p.expert_scales;
   }
+  const int n_mma = (toks + 15) & ~15;                       // UMMA N (multiple of 16, <= 256)
+  const int nblk = min(2, (p.N - n_base) / 64);              // 16x64 Marlin blocks in this channel tile
   const int total_chunks = p.K / MG_KC;
-  const bool tail = !MOE && (int)blockIdx.x >= p.full_tiles;
-  const int tail_cta = (int)blockIdx.x - p.full_tiles;
-  int u_cur = 0, u_end = 0;                                    // this CTA's range of tail k-units
-  if (tail) {
-    u_cur = (int)((long long)tail_cta * p.tail_units / p.tail_ctas);
-    u_end = (int)((long long)(tail_cta + 1) * p.tail_units / p.tail_ctas);
-  }
-  uint32_t tmem_cols = 32;                                     // the widest accumulator any segment of this CTA needs
-  {
-    const int widest = MOE ? ((moe_toks + 15) & ~15) : ((min(MG_TOK, p.M) + 15) & ~15);
-    while ((int)tmem_cols < widest) tmem_cols <<= 1;
-  }
+  const int chunk0 = blockIdx.z * p.chunks_per_split;
+  const int nchunks = min(p.chunks_per_split, total_chunks - chunk0);
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < n_mma) tmem_cols <<= 1;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < MG_MAX_STAGES; ++i) {
@@ -261,63 +242,9 @@ marlin_w4a16_tc5_kernel(const __grid_constant__ CUtensorMap tmap_a, const Marlin
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = *tmem_slot;
-  const bool prof = (p.debug & 16) && blockIdx.x == 0 && blockIdx.y == 0;
+  const bool prof = (p.debug & 16) && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
   unsigned long long w0 = 0, w1 = 0, w2 = 0, w3 = 0;
   const long long t_role0 = clock64();
-
-  for (int seg = 0;; ++seg) {
-  // ---- this segment: (tile, k-range), how many CTAs share the tile, and this CTA's slab among them ----
-  int bx = blockIdx.x, by = blockIdx.y, chunk0 = 0, nchunks = total_chunks, nseg = 1, slab_idx = 0;
-  if constexpr (!MOE) {
-    int tile = blockIdx.x;
-    if (tail) {
-      if (u_cur >= u_end) break;
-      const int upt = p.units_per_tile;
-      const int tl = u_cur / upt;
-      const int cb = u_cur - tl * upt;
-      const int ce = min(upt, cb + (u_end - u_cur));
-      u_cur += ce - cb;
-      tile = p.full_tiles + tl;
-      chunk0 = cb * p.unit_chunks;
-      nchunks = (ce - cb) * p.unit_chunks;
-      // CTA that owns k-unit v of the tail: the inverse of the range formula above
-      const int cf = (int)((((long long)tl * upt + 1) * p.tail_ctas - 1) / p.tail_units);
-      const int cl = (int)((((long long)tl * upt + upt) * p.tail_ctas - 1) / p.tail_units);
-      nseg = cl - cf + 1;
-      slab_idx = tail_cta - cf;
-    } else if (seg > 0) {
-      break;
-    }
-    bx = tile % p.tiles_x;
-    by = tile / p.tiles_x;
-  } else if (seg > 0) {
-    break;
-  }
-  if (seg > 0) {
-    // re-arm the pipeline for the next segment: every role has left the previous one (the epilogue's TMEM reads are
-    // complete: tcgen05.wait::ld), so the barriers can be invalidated and initialised afresh (phase 0)
-    tc_fence_before();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      for (int i = 0; i < MG_MAX_STAGES; ++i) {
-        mbar_inval(&full_w[i]); mbar_inval(&empty[i]); mbar_inval(&empty[MG_MAX_STAGES + i]);
-        mbar_init(&full_w[i], 5);
-        mbar_init(&empty[i], 1);
-        mbar_init(&empty[MG_MAX_STAGES + i], 1);
-      }
-      mbar_inval(accum_full);
-      mbar_init(accum_full, MG_ISSUERS);
-      *turn = 0;
-      fence_mbar_init();
-    }
-    __syncthreads();
-    tc_fence_after();
-  }
-  const int n_base = bx * MG_NT;
-  const int tok_base = MOE ? moe_tok_base : by * MG_TOK;     // first row of this segment in the TMA'd activation matrix
-  const int toks = MOE ? moe_toks : min(MG_TOK, p.M - tok_base);
-  const int n_mma = (toks + 15) & ~15;                       // UMMA N (multiple of 16, <= 256)
-  const int nblk = min(2, (p.N - n_base) / 64);              // 16x64 Marlin blocks in this channel tile
 
   // Warp roles. The two single-thread roles sit in the HIGHEST warp ids: the issue arbiter favours high warp
   // ids, and with the ALU-heavy dequant warps above them the TMA / MMA issuers were starved (measured:
@@ -631,7 +558,7 @@ marlin_w4a16_tc5_kernel(const __grid_constant__ CUtensorMap tmap_a, const Marlin
     const int ch = n_base + quad * 32 + lane;
     const bool ch_ok = ch < p.N;
     T* cptr = reinterpret_cast<T*>(p.c);
-    float* slab = (!MOE && nseg > 1) ? p.c_tmp + (size_t)slab_idx * p.M * p.N : nullptr;
+    float* slab = (!MOE && p.split_k > 1) ? p.c_tmp + (size_t)blockIdx.z * p.M * p.N : nullptr;
     // the MG_TEAMS warps that share a lane quadrant interleave 32-column slabs
     for (int col0 = team * 32; col0 < n_mma; col0 += 32 * MG_TEAMS) {
       uint32_t v[32];
@@ -660,19 +587,20 @@ marlin_w4a16_tc5_kernel(const __grid_constant__ CUtensorMap tmap_a, const Marlin
       }
     }
     if (slab != nullptr) {
-      // shared tile: every segment has stored its fp32 partial in its own slab; the LAST one to arrive (atomic ticket
-      // on the tile's lock in the reference's zeroed `workspace`) sums the slabs in segment order — deterministic, no
-      // atomics on data, no spinning and therefore no co-residency requirement between the CTAs of a tile (they may
-      // run in different waves, or beside other kernels) — writes C and returns the lock to zero
-      // (kernels/torch_bindings.cpp:167-176 contract).
+      // split-k: every split has stored its fp32 partial in its own slab; the LAST split to arrive (atomic ticket on
+      // the tile's lock in the reference's zeroed `workspace`) sums the slabs in split order — deterministic, no atomics
+      // on data, no spinning and therefore no co-residency requirement between the splits of a tile (they may run in
+      // different waves, or beside other kernels; round 1 had every split spin until all had arrived) — writes C and
+      // returns the lock to zero (kernels/torch_bindings.cpp:167-176 contract).
       constexpr int EPI = MG_DQ_WARPS * 32;
       __shared__ int s_last;
-      int* lock = p.locks + (by * p.tiles_x + bx);
+      const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+      int* lock = p.locks + tile;
       __threadfence();                                           // this thread's slab stores before the ticket
       asm volatile("bar.sync 1, %0;" ::"n"(EPI) : "memory");
       if (threadIdx.x == 0) {
         const int t = atomicAdd(lock, 1);
-        s_last = (t == nseg - 1);
+        s_last = (t == p.split_k - 1);
         if (s_last) atomicExch(lock, 0);
       }
       asm volatile("bar.sync 1, %0;" ::"n"(EPI) : "memory");
@@ -683,9 +611,15 @@ marlin_w4a16_tc5_kernel(const __grid_constant__ CUtensorMap tmap_a, const Marlin
           for (int r = warp; r < toks; r += MG_DQ_WARPS) {
             const size_t off = (size_t)(tok_base + r) * p.N + n_base + lane * 4;
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int z = 0; z < nseg; ++z) {
-              const float4 v = __ldcg(reinterpret_cast<const float4*>(p.c_tmp + (size_t)z * p.M * p.N + off));
-              acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            for (int z0 = 0; z0 < p.split_k; z0 += 4) {            // four slab loads in flight, added in split order
+              float4 v[4];
+#pragma unroll
+              for (int z = 0; z < 4; ++z)
+                v[z] = (z0 + z < p.split_k)
+                           ? __ldcg(reinterpret_cast<const float4*>(p.c_tmp + (size_t)(z0 + z) * p.M * p.N + off))
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+              for (int z = 0; z < 4; ++z) { acc.x += v[z].x; acc.y += v[z].y; acc.z += v[z].z; acc.w += v[z].w; }
             }
             uint2 o;
             o.x = pack2<T>(acc.x, acc.y);
@@ -696,9 +630,8 @@ marlin_w4a16_tc5_kernel(const __grid_constant__ CUtensorMap tmap_a, const Marlin
       }
     }
     if (prof && warp == 0 && lane == 0) g_mg_prof[15] = (unsigned long long)(clock64() - t_role0);
+    tc_fence_before();
   }
-  }   // segments
-  tc_fence_before();
   __syncthreads();
   if (warp == MG_WARP_TMA) {
     tc_fence_after();
@@ -772,46 +705,23 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-// Work plan of the dense launch (see the kernel's decoding): `full` whole tiles (complete waves, one CTA per SM: 226
-// KB of shared memory), then `tail_ctas` CTAs sharing the tiles of the last partial wave in equal contiguous ranges of
-// (tile, k-unit) pairs. A k-unit is one scale group (>= one 64-k chunk), so every range starts on a group boundary.
-struct DensePlan {
-  int full, tail_ctas, unit_chunks, units_per_tile, max_nseg;
-  long long tail_units;
-};
-static DensePlan plan_dense(int M, int N, int K, int group_size, int forced_split = 0) {
+static int plan_split_k(int M, int N, int K, int group_size) {
   const int tiles = ((N + MG_NT - 1) / MG_NT) * ((M + MG_TOK - 1) / MG_TOK);
   const int chunks = K / MG_KC;
-  int unit = group_size > MG_KC ? group_size / MG_KC : 1;
-  if (chunks % unit != 0) unit = chunks;                      // channel-wise / single group: a unit is the whole k range
-  const int upt = chunks / unit;
-  DensePlan pl{tiles, 0, unit, upt, 1, 0};
-  if ((M + MG_TOK - 1) / MG_TOK > 32) return pl;              // lock workspace (N/64*16 ints) covers <= 32 token blocks
   const int sms = num_sms();
-  int tail_tiles = 0;
-  if (forced_split > 1) {                                     // tests: every tile shared by ~forced_split CTAs
-    tail_tiles = tiles;
-    pl.full = 0;
-    pl.tail_units = (long long)tiles * upt;
-    pl.tail_ctas = (int)std::min<long long>((long long)tiles * forced_split, pl.tail_units);
-  } else {
-    const int full = tiles / sms * sms;
-    tail_tiles = tiles - full;
-    const long long units = (long long)tail_tiles * upt;
-    const int min_units = std::max(1, (8 + unit - 1) / unit);  // >= 8 chunks of work per CTA
-    const long long g = std::min<long long>(sms, units / min_units);
-    // worth it only if the tail wave would be visibly under-filled and the ranges are shorter than a tile
-    if (tail_tiles == 0 || tail_tiles * 10 >= sms * 9 || g <= tail_tiles) return pl;
-    pl.full = full;
-    pl.tail_units = units;
-    pl.tail_ctas = (int)g;
+  if ((M + MG_TOK - 1) / MG_TOK > 32) return 1;   // lock workspace (N/64*16 ints) covers <= 32 token blocks
+  // as many k-splits as fit one wave of the SMs (one CTA per SM) with at least 8 chunks each: 48 tiles -> 3 splits =
+  // 144 CTAs (a power-of-two rule left a third of the SMs idle)
+  int split = std::min(sms / std::max(tiles, 1), chunks / 8);
+  if (split < 1) split = 1;
+  // keep every split on a group boundary and none empty
+  const int gchunks = group_size > MG_KC ? group_size / MG_KC : 1;
+  for (; split > 1; --split) {
+    int per = (chunks + split - 1) / split;
+    per = (per + gchunks - 1) / gchunks * gchunks;
+    if ((split - 1) * per < chunks) break;
   }
-  for (int t = 0; t < tail_tiles; ++t) {
-    const int cf = (int)((((long long)t * upt + 1) * pl.tail_ctas - 1) / pl.tail_units);
-    const int cl = (int)((((long long)t * upt + upt) * pl.tail_ctas - 1) / pl.tail_units);
-    pl.max_nseg = std::max(pl.max_nseg, cl - cf + 1);
-  }
-  return pl;
+  return split;
 }
 
 template <typename T, int ZP, int BITS, bool MOE, bool RING>
@@ -947,19 +857,9 @@ extern "C" int b200_debug_marlin_prof(unsigned long long* out32) {
 extern "C" int b200_marlin_gemm_plan(int size_m, int size_n, int size_k, int num_groups) {
   const int gs = num_groups > 1 ? size_k / num_groups : -1;
   if (size_m <= 0 || size_n <= 0 || size_k < MG_KC) return 1;
-  int split = plan_dense(size_m, size_n, size_k, gs).max_nseg;
+  int split = plan_split_k(size_m, size_n, size_k, gs);
   if (size_m <= MG_SMALL_M) split = std::max(split, marlin_small_plan(size_m, size_n, size_k, gs));
   return split;
-}
-
-// the dense launch's work plan for a shape (what b200_gptq_marlin_gemm launches with split_k <= 0, size_m > 32):
-// out5 = {whole tiles, tail CTAs, chunks per k-unit, k-units per tile, max CTAs sharing one tile}. Pure host arithmetic.
-extern "C" int b200_marlin_dense_plan(int size_m, int size_n, int size_k, int num_groups, int* out5) {
-  B200_CHECK(out5 != nullptr && size_m > 0 && size_n > 0 && size_k >= MG_KC, "marlin_dense_plan: bad arguments");
-  const int gs = num_groups > 1 ? size_k / num_groups : -1;
-  const DensePlan pl = plan_dense(size_m, size_n, size_k, gs);
-  out5[0] = pl.full; out5[1] = pl.tail_ctas; out5[2] = pl.unit_chunks; out5[3] = pl.units_per_tile; out5[4] = pl.max_nseg;
-  return 0;
 }
 
 extern "C" int b200_gptq_marlin_gemm(const void* a, const void* b_q_weight, const void* b_scales,
@@ -984,14 +884,15 @@ extern "C" int b200_gptq_marlin_gemm(const void* a, const void* b_q_weight, cons
   if (num_bits == 4 && has_zp != ZP_FLOAT && size_m <= MG_SMALL_M && marlin_use_small())
     return marlin_small_gemm(a, b_q_weight, b_scales, b_zeros, c, c_tmp, workspace, size_m, size_n, size_k, num_groups,
                              has_zp, dtype, split_k, (cudaStream_t)stream);
-  // split_k <= 0: the planner decides; split_k == 1: whole tiles only; split_k > 1: every tile shared that many ways (tests)
-  DensePlan plan = plan_dense(size_m, size_n, size_k, gs, split_k > 1 ? split_k : 0);
-  if (split_k == 1) {
-    plan.full = ((size_n + MG_NT - 1) / MG_NT) * ((size_m + MG_TOK - 1) / MG_TOK);
-    plan.tail_ctas = 0; plan.tail_units = 0; plan.max_nseg = 1;
+  if (split_k <= 0) split_k = plan_split_k(size_m, size_n, size_k, gs);
+  B200_CHECK(split_k == 1 || (c_tmp != nullptr && workspace != nullptr),
+             "split-k needs the fp32 partial buffer [split_k, M, N] and the zeroed lock workspace");
+  {
+    const int tiles = ((size_n + MG_NT - 1) / MG_NT) * ((size_m + MG_TOK - 1) / MG_TOK);
+    while (split_k > 1 && tiles * split_k > num_sms()) --split_k;   // one wave
+    const int chunks_total = size_k / MG_KC;
+    while (split_k > 1 && (split_k - 1) * ((chunks_total + split_k - 1) / split_k) >= chunks_total) --split_k;
   }
-  B200_CHECK(plan.max_nseg == 1 || (c_tmp != nullptr && workspace != nullptr),
-             "shared tiles need the fp32 partial buffer [plan, M, N] and the zeroed lock workspace");
   const int toks = size_m < MG_TOK ? size_m : MG_TOK;
   const int box_rows = (toks + 15) & ~15;
   CUtensorMap tmap;
@@ -999,16 +900,23 @@ extern "C" int b200_gptq_marlin_gemm(const void* a, const void* b_q_weight, cons
   MarlinParams p{};
   p.b_q = (const uint32_t*)b_q_weight; p.scales = b_scales; p.zeros = b_zeros;
   p.c = c; p.c_tmp = c_tmp; p.locks = workspace; p.M = size_m; p.N = size_n; p.K = size_k;
+  p.split_k = split_k;
   p.box_rows = box_rows;
   p.act_bytes = (box_rows * 128 + 1023) & ~1023;
   fill_group_params(p, size_k, gs);
-  p.tiles_x = (size_n + MG_NT - 1) / MG_NT;
-  p.full_tiles = plan.full;
-  p.tail_ctas = plan.tail_ctas;
-  p.unit_chunks = plan.unit_chunks;
-  p.units_per_tile = plan.units_per_tile;
-  p.tail_units = plan.tail_units;
-  dim3 grid(plan.full + plan.tail_ctas, 1, 1);
+  const int chunks = size_k / MG_KC;
+  {
+    const int gchunks = gs > MG_KC ? gs / MG_KC : 1;
+    int per = (chunks + split_k - 1) / split_k;
+    per = (per + gchunks - 1) / gchunks * gchunks;            // splits start on group boundaries
+    while (split_k > 1 && (split_k - 1) * per >= chunks) {    // never an empty split
+      --split_k;
+      per = ((chunks + split_k - 1) / split_k + gchunks - 1) / gchunks * gchunks;
+    }
+    p.split_k = split_k;
+    p.chunks_per_split = per;
+  }
+  dim3 grid((size_n + MG_NT - 1) / MG_NT, (size_m + MG_TOK - 1) / MG_TOK, split_k);
   return dispatch_marlin<false>(tmap, p, grid, dtype, has_zp, num_bits, (cudaStream_t)stream);
 }
 
@@ -1057,9 +965,11 @@ extern "C" int b200_marlin_gemm_moe(const void* a, const void* b_q_weights, cons
   MarlinParams p{};
   p.b_q = (const uint32_t*)b_q_weights; p.scales = b_scales; p.zeros = nullptr;
   p.c = c; p.M = valid_rows; p.N = size_n; p.K = size_k;
+  p.split_k = 1;
   p.box_rows = tile_rows;
   p.act_bytes = (tile_rows * 128 + 1023) & ~1023;
   fill_group_params(p, size_k, gs);
+  p.chunks_per_split = size_k / MG_KC;
   p.expert_offsets = expert_offsets; p.sorted_ids = sorted_ids;
   p.topk_weights = apply_weights ? topk_weights : nullptr;
   p.num_experts = num_experts; p.valid_rows = valid_rows; p.tile_rows = tile_rows;

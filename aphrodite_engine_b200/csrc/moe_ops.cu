@@ -12,6 +12,8 @@
 // thread count (256) is independent of E and the counter matrix is (T+1) x E.
 #include "common.cuh"
 
+#include <algorithm>
+
 namespace b200 {
 
 template <typename I>
@@ -109,6 +111,36 @@ topk_softmax_kernel(const float* __restrict__ gating, float* __restrict__ weight
   }
 }
 
+// final[t, :] (+)= T(cur[t, :] * w_e[t]),  w_e[t] = sum_k topk_weights[t, k] * (topk_ids[t, k] == expert)
+// The expert loop body of the reference's dense-per-expert MoE (aphrodite/modeling/models/mixtral_quant.py:141-152:
+// expert_mask -> expert_weights -> current.mul_(expert_weights) -> final.add_(current)) as one pass: the product is
+// formed in fp32 and rounded to T (in-place mul_ of a 16-bit tensor by an fp32 one), the accumulation is a T add.
+template <typename T>
+__global__ void __launch_bounds__(256)
+moe_expert_scale_add_kernel(T* __restrict__ final_out, const T* __restrict__ cur, const float* __restrict__ topk_weights,
+                            const int32_t* __restrict__ topk_ids, int num_tokens, int hidden, int topk, int expert,
+                            int first) {
+  constexpr int N = 16 / sizeof(T);
+  const int per_tok = hidden / N;
+  const int64_t total = (int64_t)num_tokens * per_tok;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t tok = idx / per_tok;
+    float w = 0.f;
+    for (int k = 0; k < topk; ++k)
+      w += (topk_ids[tok * topk + k] == expert) ? topk_weights[tok * topk + k] : 0.f;
+    union { uint4 raw; T e[N]; } c, f;
+    c.raw = __ldg(reinterpret_cast<const uint4*>(cur) + idx);
+    if (!first) f.raw = reinterpret_cast<const uint4*>(final_out)[idx];
+#pragma unroll
+    for (int e = 0; e < N; ++e) {
+      const T scaled = from_f32<T>(__fmul_rn(to_f32<T>(c.e[e]), w));
+      f.e[e] = first ? scaled : from_f32<T>(__fadd_rn(to_f32<T>(f.e[e]), to_f32<T>(scaled)));
+    }
+    reinterpret_cast<uint4*>(final_out)[idx] = f.raw;
+  }
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -147,4 +179,24 @@ extern "C" int b200_topk_softmax(float* topk_weights, int32_t* topk_indices, int
   topk_softmax_kernel<<<(num_tokens + warps - 1) / warps, warps * 32, smem, (cudaStream_t)stream>>>(
       gating_output, topk_weights, topk_indices, token_expert_indices, num_tokens, num_experts, topk);
   return check_launch("topk_softmax_kernel");
+}
+
+extern "C" int b200_moe_expert_scale_add(void* final_out, const void* cur, const float* topk_weights,
+                                         const int32_t* topk_ids, int num_tokens, int hidden, int topk, int expert,
+                                         int first, int dtype, void* stream) {
+  B200_CHECK(dtype == B200_F16 || dtype == B200_BF16, "moe_expert_scale_add: float16 / bfloat16 only");
+  B200_CHECK(hidden % 8 == 0 && ((reinterpret_cast<uintptr_t>(final_out) | reinterpret_cast<uintptr_t>(cur)) & 15) == 0,
+             "moe_expert_scale_add: rows must be 16-byte aligned multiples of 8 elements");
+  if (num_tokens == 0) return 0;
+  const int64_t work = (int64_t)num_tokens * (hidden / 8);
+  const int grid = (int)std::min<int64_t>((work + 255) / 256, (int64_t)num_sms() * 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == B200_BF16)
+    moe_expert_scale_add_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((__nv_bfloat16*)final_out, (const __nv_bfloat16*)cur,
+                                                                    topk_weights, topk_ids, num_tokens, hidden, topk,
+                                                                    expert, first);
+  else
+    moe_expert_scale_add_kernel<__half><<<grid, 256, 0, st>>>((__half*)final_out, (const __half*)cur, topk_weights,
+                                                             topk_ids, num_tokens, hidden, topk, expert, first);
+  return check_launch("moe_expert_scale_add_kernel");
 }

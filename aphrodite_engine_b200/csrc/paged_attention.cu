@@ -22,6 +22,7 @@
 // with ALiBi ...) run on a generic SIMT kernel in this file — still on the GPU; there is no CPU path.
 #include "common.cuh"
 
+#include <algorithm>
 #include <float.h>
 #include <math.h>
 
@@ -46,6 +47,7 @@ struct AttnParams {
   int num_seqs, num_heads, num_kv_heads, head_size, block_size;
   int max_num_blocks_per_seq;
   int max_num_partitions;  // 0 for v1
+  int max_seq_len;         // caller's bound on seq_lens (v1: sizes the cluster split; <= 0: unknown)
   int64_t q_stride, kv_block_stride, kv_head_stride;
   float scale, k_scale, v_scale;
   int tp_rank, bs_local_blocks, bs_vert_stride, bs_block_size, bs_head_sliding_step;
@@ -122,6 +124,33 @@ template <> __device__ __forceinline__ uint32_t pair_to_f16<__nv_bfloat16>(uint3
   return pack2<__half>(lo, hi);
 }
 
+// ---- thread-block cluster helpers: a v1 launch may split every sequence over the CTAs of a cluster (1, 1, cs) ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void st_cluster_f32(const float* local_ptr, uint32_t cta_rank, float v) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local_ptr)), "r"(cta_rank));
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(v) : "memory");
+}
+static constexpr int kMaxClusterSplit = 4;
+
+// Non-partitioned launches may run as clusters of cs CTAs along z: CTA r of a cluster takes the r-th share of the
+// sequence's blocks, the partial (max, sum, O) of every CTA is written into the LEADER's shared memory through DSMEM
+// and merged there in fp32 — the split-KV idea of paged_attention_v2 without its global scratch, second kernel or
+// 16-bit rounding of the partial outputs. It exists for wave quantisation: (kv-heads x seqs) CTAs at 2 per SM run in
+// ceil(n / 296) waves, and e.g. 1024 CTAs (BASELINE configs[3] per GPU: 1 kv-head, 1024 seqs) are 3.46 waves = 86 %
+// of the HBM roofline at best; as 2048 half-length CTAs they are 6.9 waves = 99 %.
 template <typename T, int D, int BS, int KV, bool PARTITIONED>
 __global__ void __launch_bounds__(kFastThreads, 2)
 paged_attention_tc_kernel(const AttnParams p) {
@@ -142,7 +171,7 @@ paged_attention_tc_kernel(const AttnParams p) {
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int seq = blockIdx.y;
-  const int part = PARTITIONED ? blockIdx.z : 0;
+  const int part_idx = PARTITIONED ? blockIdx.z : 0;
   const int G = p.num_heads / p.num_kv_heads;        // q-heads per kv-head
   const int groups = (G + kHeadsPerCta - 1) / kHeadsPerCta;
   const int kvh = blockIdx.x / groups;
@@ -151,12 +180,18 @@ paged_attention_tc_kernel(const AttnParams p) {
   const int nheads = min(kHeadsPerCta, G - hgrp * kHeadsPerCta);
 
   const int seq_len = p.seq_lens[seq];
-  if (PARTITIONED && part * kPartitionSize >= seq_len) return;  // nothing to do (reference :117-120)
+  if (PARTITIONED && part_idx * kPartitionSize >= seq_len) return;  // nothing to do (reference :117-120)
 
   const int num_seq_blocks = (seq_len + BS - 1) / BS;
-  const int start_block = PARTITIONED ? part * (kPartitionSize / BS) : 0;
-  const int end_block =
-      PARTITIONED ? min(start_block + kPartitionSize / BS, num_seq_blocks) : num_seq_blocks;
+  const uint32_t cs = PARTITIONED ? 1u : cluster_nctarank();     // CTAs sharing this sequence (1: plain launch)
+  const uint32_t crank = PARTITIONED ? 0u : cluster_ctarank();
+  int start_block = PARTITIONED ? part_idx * (kPartitionSize / BS) : 0;
+  int end_block = PARTITIONED ? min(start_block + kPartitionSize / BS, num_seq_blocks) : num_seq_blocks;
+  if (!PARTITIONED && cs > 1) {
+    const int per = (num_seq_blocks + (int)cs - 1) / (int)cs;
+    start_block = (int)crank * per;
+    end_block = min(start_block + per, num_seq_blocks);
+  }
   const int nblocks = max(end_block - start_block, 0);
 
   if (threadIdx.x == 0) {
@@ -397,6 +432,9 @@ paged_attention_tc_kernel(const AttnParams p) {
   __syncthreads();
 
   T* outp = reinterpret_cast<T*>(p.out);
+  // cluster launch: every CTA's ring is free now (its own merge buffer lives there), so peers may write into the leader
+  if (!PARTITIONED && cs > 1) cluster_sync_all();
+  float* part = mo + kConsumerWarps * kHeadsPerCta * Cfg::OPAD;   // leader: [cs][8 heads][OPAD], cols D / D+1 = (m, l)
   for (int idx = threadIdx.x; idx < nheads * D; idx += kFastThreads) {
     const int h = idx / D, d = idx % D;
     float mg = -INFINITY;
@@ -411,11 +449,20 @@ paged_attention_tc_kernel(const AttnParams p) {
         den += f * merge_l[w * kHeadsPerCta + h];
       }
     }
+    if (!PARTITIONED && cs > 1) {
+      float* slot = part + ((int)crank * kHeadsPerCta + h) * Cfg::OPAD;
+      st_cluster_f32(slot + d, 0, num);
+      if (d == 0) {
+        st_cluster_f32(slot + D, 0, mg);
+        st_cluster_f32(slot + D + 1, 0, den);
+      }
+      continue;
+    }
     float val = num * __fdividef(1.f, den + 1e-6f);
     if (KV != B200_KV_AUTO) val *= p.v_scale;
     const int head = head0 + h;
     if (PARTITIONED) {
-      const int64_t base = ((int64_t)seq * p.num_heads + head) * p.max_num_partitions + part;
+      const int64_t base = ((int64_t)seq * p.num_heads + head) * p.max_num_partitions + part_idx;
       outp[base * D + d] = from_f32<T>(val);
       if (d == 0) {
         p.max_logits[base] = (mg == -INFINITY) ? -FLT_MAX : mg * kLn2;
@@ -423,6 +470,28 @@ paged_attention_tc_kernel(const AttnParams p) {
       }
     } else {
       outp[((int64_t)seq * p.num_heads + head) * D + d] = from_f32<T>(val);
+    }
+  }
+  if (!PARTITIONED && cs > 1) {
+    cluster_sync_all();                       // all partials have landed in the leader's shared memory
+    if (crank == 0) {
+      for (int idx = threadIdx.x; idx < nheads * D; idx += kFastThreads) {
+        const int h = idx / D, d = idx % D;
+        float mg = -INFINITY;
+        for (uint32_t r = 0; r < cs; ++r) mg = fmaxf(mg, part[(r * kHeadsPerCta + h) * Cfg::OPAD + D]);
+        float num = 0.f, den = 0.f;
+        if (mg != -INFINITY) {
+          for (uint32_t r = 0; r < cs; ++r) {
+            const float* slot = part + (r * kHeadsPerCta + h) * Cfg::OPAD;
+            const float f = fast_exp2(slot[D] - mg);
+            num += f * slot[d];
+            den += f * slot[D + 1];
+          }
+        }
+        float val = num * __fdividef(1.f, den + 1e-6f);
+        if (KV != B200_KV_AUTO) val *= p.v_scale;
+        outp[((int64_t)seq * p.num_heads + head0 + h) * D + d] = from_f32<T>(val);
+      }
     }
   }
 }
@@ -457,16 +526,16 @@ paged_attention_generic_kernel(const AttnParams p) {
   __shared__ float bcast;
 
   const int head = blockIdx.x, seq = blockIdx.y;
-  const int part = PARTITIONED ? blockIdx.z : 0;
+  const int part_idx = PARTITIONED ? blockIdx.z : 0;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int seq_len = p.seq_lens[seq];
-  if (PARTITIONED && part * kPartitionSize >= seq_len) return;
+  if (PARTITIONED && part_idx * kPartitionSize >= seq_len) return;
   const int G = p.num_heads / p.num_kv_heads;
   const int kvh = head / G;
   constexpr int ESZ = (KV == B200_KV_AUTO) ? (int)sizeof(T) : 1;
   const int x = 16 / ESZ;
 
-  const int tok_begin = PARTITIONED ? part * kPartitionSize : 0;
+  const int tok_begin = PARTITIONED ? part_idx * kPartitionSize : 0;
   const int tok_end = PARTITIONED ? min(tok_begin + kPartitionSize, seq_len) : seq_len;
 
   const T* qp = reinterpret_cast<const T*>(p.q) + (int64_t)seq * p.q_stride + (int64_t)head * D;
@@ -579,7 +648,7 @@ paged_attention_generic_kernel(const AttnParams p) {
   T* outp = reinterpret_cast<T*>(p.out);
   int64_t obase;
   if (PARTITIONED) {
-    const int64_t b = ((int64_t)seq * p.num_heads + head) * p.max_num_partitions + part;
+    const int64_t b = ((int64_t)seq * p.num_heads + head) * p.max_num_partitions + part_idx;
     obase = b * D;
     if (tid == 0) {
       p.max_logits[b] = m_run;
@@ -646,6 +715,7 @@ paged_attention_reduce_kernel(T* __restrict__ out, const float* __restrict__ exp
 // =================================================================================================
 static thread_local int g_force_impl = 0;
 static thread_local int g_last_path = 0;
+static thread_local int g_last_cluster_split = 1;
 
 template <typename T, int D, int BS, int KV, bool PART>
 static int launch_tc(const AttnParams& p, cudaStream_t st) {
@@ -662,7 +732,41 @@ static int launch_tc(const AttnParams& p, cudaStream_t st) {
   const int G = p.num_heads / p.num_kv_heads;
   const int groups = (G + kHeadsPerCta - 1) / kHeadsPerCta;
   dim3 grid(p.num_kv_heads * groups, p.num_seqs, PART ? p.max_num_partitions : 1);
-  kern<<<grid, kFastThreads, Cfg::SMEM_BYTES, st>>>(p);
+  int cs = 1;
+  if constexpr (!PART) {
+    // split every sequence over a cluster of cs CTAs when that fills the waves of 2 CTAs per SM visibly better
+    // (and every CTA still streams >= 64 blocks); g_force_impl 2 / 4 force a split (tests)
+    const long long n = (long long)grid.x * grid.y, resident = 2LL * num_sms();
+    const int max_blocks = p.max_seq_len > 0 ? std::min((p.max_seq_len + BS - 1) / BS, p.max_num_blocks_per_seq)
+                                             : p.max_num_blocks_per_seq;
+    auto eff = [&](int c) { const long long m = n * c; return (double)m / (double)(((m + resident - 1) / resident) * resident); };
+    auto fits = [&](int c) { return Cfg::MERGE_BYTES + c * kHeadsPerCta * Cfg::OPAD * 4 <= Cfg::DATA_BYTES; };
+    if (g_force_impl == 2 || g_force_impl == 4) {
+      cs = fits(g_force_impl) ? g_force_impl : 1;
+    } else {
+      for (int c = 2; c <= kMaxClusterSplit; c *= 2)
+        if (fits(c) && max_blocks / c >= 64 && eff(c) > eff(cs) + 0.04) cs = c;
+    }
+  }
+  if (cs == 1) {
+    kern<<<grid, kFastThreads, Cfg::SMEM_BYTES, st>>>(p);
+  } else {
+    grid.z = cs;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kFastThreads, 1, 1);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = cs;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    B200_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, p));
+  }
+  g_last_cluster_split = cs;
   return check_launch("paged_attention_tc_kernel");
 }
 
@@ -782,6 +886,7 @@ extern "C" int b200_set_attention_impl(int impl) {
   return prev;
 }
 extern "C" int b200_last_attention_path(void) { return g_last_path; }
+extern "C" int b200_last_attention_cluster_split(void) { return g_last_cluster_split; }
 
 extern "C" int b200_paged_attention_v1(
     void* out, const void* query, const void* key_cache, const void* value_cache, int num_seqs,
@@ -791,8 +896,8 @@ extern "C" int b200_paged_attention_v1(
     int64_t kv_head_stride, int dtype, int kv_dtype, float k_scale, float v_scale, int tp_rank,
     int blocksparse_local_blocks, int blocksparse_vert_stride, int blocksparse_block_size,
     int blocksparse_head_sliding_step, void* stream) {
-  (void)max_seq_len;  // the reference sizes its logits buffer with it; the online softmax does not
   AttnParams p{};
+  p.max_seq_len = max_seq_len;  // the reference sizes its logits buffer with it; here it only guides the cluster split
   p.out = out; p.q = query; p.k_cache = key_cache; p.v_cache = value_cache;
   p.block_tables = block_tables; p.seq_lens = seq_lens; p.alibi_slopes = alibi_slopes;
   p.num_seqs = num_seqs; p.num_heads = num_heads; p.num_kv_heads = num_kv_heads;

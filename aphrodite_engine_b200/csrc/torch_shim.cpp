@@ -626,6 +626,18 @@ void rotary_embedding_and_cache(torch::Tensor& positions, torch::Tensor& query, 
       (int)key_cache.size(4), dtype_code(query, "rotary_embedding_and_cache"), kv_code(kv_cache_dtype), (float)k_scale,
       (float)v_scale, cur_stream()));
 }
+void moe_expert_scale_add(torch::Tensor& final_out, torch::Tensor& cur, torch::Tensor& topk_weights,
+                          torch::Tensor& topk_ids, int64_t expert, bool first) {
+  const at::cuda::OptionalCUDAGuard guard(device_of(cur));
+  TORCH_CHECK(final_out.is_contiguous() && cur.is_contiguous() && final_out.sizes() == cur.sizes() && cur.dim() == 2 &&
+              final_out.scalar_type() == cur.scalar_type(), "moe_expert_scale_add: final / cur must be contiguous [T, H]");
+  TORCH_CHECK(topk_weights.scalar_type() == at::kFloat && topk_ids.scalar_type() == at::kInt &&
+              topk_weights.is_contiguous() && topk_ids.is_contiguous() && topk_weights.sizes() == topk_ids.sizes() &&
+              topk_ids.size(0) == cur.size(0), "moe_expert_scale_add: topk_weights f32 / topk_ids int32 [T, topk]");
+  check(b200_moe_expert_scale_add(final_out.data_ptr(), cur.data_ptr(), topk_weights.data_ptr<float>(),
+                                  topk_ids.data_ptr<int>(), (int)cur.size(0), (int)cur.size(1), (int)topk_ids.size(1),
+                                  (int)expert, first ? 1 : 0, dtype_code(cur, "moe_expert_scale_add"), cur_stream()));
+}
 int64_t tp_flag_bytes() { return b200_tp_flag_bytes(); }
 
 }  // namespace
@@ -796,6 +808,9 @@ TORCH_LIBRARY(_C_b200, ext) {
       "Tensor!? residual, Tensor? weight, float epsilon, int flag_off, int rank, int world, int algo) -> ()");
   ext.impl("tp_allreduce_rows", torch::kCUDA, &tp_allreduce_rows);
   ext.def("tp_flag_bytes", &tp_flag_bytes);
+  ext.def("moe_expert_scale_add(Tensor! final_out, Tensor cur, Tensor topk_weights, Tensor topk_ids, int expert, "
+          "bool first) -> ()");
+  ext.impl("moe_expert_scale_add", torch::kCUDA, &moe_expert_scale_add);
   ext.def(
       "rotary_embedding_and_cache(Tensor positions, Tensor! query, Tensor! key, Tensor value, int head_size, "
       "Tensor cos_sin_cache, bool is_neox, Tensor! key_cache, Tensor! value_cache, Tensor slot_mapping, "

@@ -74,7 +74,8 @@ class LlamaDecoder:
                  tp_size: int = 1, group=None, seed: int = 1234, layers: Optional[int] = None,
                  kv_fill: bool = True, quant: Optional[str] = None, group_size: int = 128,
                  custom_ar=None, nvls=None, op_table=None, attention_cls=None, share_from: "LlamaDecoder" = None,
-                 fuse_rope_cache: Optional[bool] = None):
+                 fuse_rope_cache: Optional[bool] = None, share_kv_from: "LlamaDecoder" = None,
+                 share_weights_from: "LlamaDecoder" = None):
         assert shape.heads % tp_size == 0 and shape.kv_heads % tp_size == 0
         assert shape.intermediate % tp_size == 0 and shape.vocab % tp_size == 0
         self.s, self.batch, self.block_size = shape, batch, block_size
@@ -110,8 +111,20 @@ class LlamaDecoder:
             self.embed, self.layers, self.norm, self.lm_head = o.embed, o.layers, o.norm, o.lm_head
             self.cos_sin, self.kv_caches, self.kv_views = o.cos_sin, o.kv_caches, o.kv_views
         else:
-            self._init_weights(seed, group_size)
-            self._init_kv_cache(num_blocks, kv_fill, seed)
+            # share_weights_from: same parameters over another KV cache (other batch / context / cache dtype);
+            # share_kv_from: same cache, embedding, head and norms, other linear weights (e.g. the quantised variant)
+            if share_weights_from is not None:
+                o = share_weights_from
+                assert (o.tp_size, o.tp_rank, o.quant, o.n_layers) == (tp_size, tp_rank, quant, self.n_layers)
+                self.embed, self.layers, self.norm, self.lm_head, self.cos_sin = o.embed, o.layers, o.norm, o.lm_head, o.cos_sin
+            else:
+                self._init_weights(seed, group_size, reuse=share_kv_from)
+            if share_kv_from is not None:
+                o = share_kv_from
+                assert (o.tp_size, o.tp_rank, o.n_layers, o.kv_cache_dtype) == (tp_size, tp_rank, self.n_layers, kv_cache_dtype)
+                self.kv_caches, self.kv_views = o.kv_caches, o.kv_views
+            else:
+                self._init_kv_cache(num_blocks, kv_fill, seed)
         # norm x2 (or 2 fused exchanges), rope, cache write (one launch when fused), attention, act (+ 4 W4A16 GEMMs)
         per_layer = 6 - (1 if self.fuse_rope_cache else 0) + (4 if quant == "gptq" else 0)
         if self.tp_mode == "p2p":
@@ -119,7 +132,7 @@ class LlamaDecoder:
         self.my_kernel_launches_per_step = per_layer * self.n_layers + 1
 
     # ------------------------------------------------------------------------------------------------------------
-    def _init_weights(self, seed: int, group_size: int):
+    def _init_weights(self, seed: int, group_size: int, reuse: "LlamaDecoder" = None):
         s, dev, dtype, r, n = self.s, self.device, self.dtype, self.tp_rank, self.tp_size
         g = torch.Generator(device=dev).manual_seed(seed)
         H = s.hidden
@@ -178,7 +191,7 @@ class LlamaDecoder:
             def row_parallel(n_out, k_in):
                 return cols(full(n_out, k_in))
 
-        self.embed = full(s.vocab, H)
+        self.embed = full(s.vocab, H) if reuse is None else reuse.embed
         QS, KS, I = s.heads * s.head_size, s.kv_heads * s.head_size, s.intermediate
         self.layers = []
         for _ in range(self.n_layers):
@@ -191,7 +204,7 @@ class LlamaDecoder:
                 down=row_parallel(H, I),
             ))
         self.norm = torch.ones(H, dtype=dtype, device=dev)
-        self.lm_head = rows(full(s.vocab, H), (s.vocab,))
+        self.lm_head = rows(full(s.vocab, H), (s.vocab,)) if reuse is None else reuse.lm_head
         # rotary cache [max_pos, rot_dim] = cat(cos, sin) (modeling/layers/rotary_embedding.py:105-120)
         inv = 1.0 / (s.rope_theta ** (torch.arange(0, s.head_size, 2, dtype=torch.float32) / s.head_size))
         fr = torch.einsum("i,j->ij", torch.arange(s.max_position, dtype=torch.float32), inv)

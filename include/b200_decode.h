@@ -75,12 +75,16 @@ int b200_paged_attention_v2(
     int tp_rank, int blocksparse_local_blocks, int blocksparse_vert_stride,
     int blocksparse_block_size, int blocksparse_head_sliding_step, void* stream);
 
-/* Selects the implementation for the two calls above (debug / A-B measurement):
- *   0 = auto (tensor-core bulk-copy kernel when the shape allows, generic SIMT kernel otherwise)
- *   1 = force the generic SIMT kernel.  Returns the previous value. */
+/* Selects the implementation for the two calls above (tests / A-B measurement):
+ *   0 = auto (tensor-core bulk-copy kernel when the shape allows, generic SIMT kernel otherwise; v1 launches split
+ *       every sequence over a thread-block cluster when that fills the GPU's waves visibly better)
+ *   1 = force the generic SIMT kernel;  2 / 4 = force a cluster split of 2 / 4 CTAs per sequence (v1).
+ * Returns the previous value. */
 int b200_set_attention_impl(int impl);
 /* 1 if the last paged_attention call on this thread took the tensor-core path, else 0 */
 int b200_last_attention_path(void);
+/* CTAs per sequence (cluster size) of the last tensor-core v1 launch on this thread */
+int b200_last_attention_cluster_split(void);
 
 /* ---- cache ops ------------------------------------------------------------------------------
  * replaces reshape_and_cache       kernels/cache_kernels.cu:263-289 (schema torch_bindings.cpp:467-473)
@@ -179,11 +183,6 @@ int b200_activation(void* out, const void* input, int num_tokens, int d, int act
  * partition ignores split_k. Act-order with the full k range is handled by the caller
  * permuting A's columns (b200_permute_cols), as the reference does with a_tmp (gptq_marlin.cu:2145-2158). */
 int b200_marlin_gemm_plan(int size_m, int size_n, int size_k, int num_groups);
-/* The dense launch's work plan for a shape (size_m > 32): out5 = {whole tiles, tail CTAs, 64-k chunks per k-unit,
- * k-units per tile, max CTAs sharing one tile}. Whole tiles fill complete waves of the SMs; the tiles of the last
- * partial wave are shared by `tail CTAs` in equal contiguous (tile, k-unit) ranges, each shared tile reduced through
- * fp32 slabs by the last CTA to arrive on the tile's lock (segment order, deterministic). Host arithmetic only. */
-int b200_marlin_dense_plan(int size_m, int size_n, int size_k, int num_groups, int* out5);
 /* debug only: per-role cycle attribution of the last GEMM launched with B200_MARLIN_DEBUG & 16 (32 x u64) */
 int b200_debug_marlin_prof(unsigned long long* out32);
 int b200_gptq_marlin_gemm(const void* a, const void* b_q_weight, const void* b_scales,
@@ -225,6 +224,14 @@ int b200_moe_align_block_size(const void* topk_ids, int ids_are_int64, int64_t n
 /* gating_output fp32 [num_tokens, num_experts]; outputs [num_tokens, topk] */
 int b200_topk_softmax(float* topk_weights, int32_t* topk_indices, int32_t* token_expert_indices,
                       const float* gating_output, int num_tokens, int num_experts, int topk, void* stream);
+
+/* Expert-loop body of the reference's dense-per-expert quantised MoE (aphrodite/modeling/models/mixtral_quant.py:141-152)
+ * as one pass (extension; torch op _C_b200::moe_expert_scale_add):
+ *   final[t,:] = first ? T(cur[t,:] * w[t]) : T(final[t,:] + T(cur[t,:] * w[t])),
+ *   w[t] = sum_k topk_weights[t,k] * (topk_ids[t,k] == expert)        (fp32)
+ * final / cur [num_tokens, hidden] f16/bf16; topk_weights f32 and topk_ids int32 [num_tokens, topk]. */
+int b200_moe_expert_scale_add(void* final_out, const void* cur, const float* topk_weights, const int32_t* topk_ids,
+                              int num_tokens, int hidden, int topk, int expert, int first, int dtype, void* stream);
 
 /* ---- custom all-reduce over NVLink peer memory ---------------------------------------------------
  * replaces init_custom_ar / all_reduce_reg / all_reduce_unreg / dispose / meta_size / register_buffer /

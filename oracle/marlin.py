@@ -281,3 +281,27 @@ def fused_marlin_moe(a: torch.Tensor, w1_refs, w2_refs, topk_weights: torch.Tens
     act = po.silu_and_mul(gate_up.view(M * topk, -1))
     down = marlin_gemm_moe(act, w2_refs, topk_ids, topk_weights, False, True)
     return torch.sum(down, dim=1)
+
+
+def mixtral_quant_moe(x: torch.Tensor, gate_w: torch.Tensor, w13_refs: dict, w2_refs: dict, topk: int,
+                      experts) -> torch.Tensor:
+    """aphrodite/modeling/models/mixtral_quant.py:128-152 (one rank's partial sum, before the all-reduce), with the
+    experts' dequantised weights: w13_refs[e] [H, 2I] (w1 | w3 side by side), w2_refs[e] [I, H].
+    router: softmax in fp32 -> top-k -> renormalise (:133-139); per local expert: dense MLP on ALL tokens (:82-88,
+    SiLU(w1 x) * (w3 x) with every op rounding to the activation dtype), `.mul_(expert_weights)` (:148, the product
+    formed in fp32, rounded once), `final.add_(current)` (:152, an activation-dtype add)."""
+    from oracle import paged_ops as po
+    dt = x.dtype
+    logits = (x.float() @ gate_w.float().t()).to(dt)
+    p = torch.softmax(logits.float(), dim=1)
+    w, ids = torch.topk(p, topk, dim=-1)
+    w = w / w.sum(dim=-1, keepdim=True)
+    final = None
+    for e in experts:
+        gate_up = marlin_gemm(x, w13_refs[e])
+        act = po.silu_and_mul(gate_up)
+        cur = marlin_gemm(act, w2_refs[e])
+        ew = (w * (ids == e)).sum(dim=-1, keepdim=True)
+        cur = (cur.float() * ew).to(dt)
+        final = cur if final is None else (final.float() + cur.float()).to(dt)
+    return final

@@ -228,3 +228,44 @@ def test_full_size_properties(ops):
     ref = po.paged_attention(q[pick].cpu(), kc[blocks].cpu(), vc[blocks].cpu(), bt_small,
                              sl[pick].cpu(), scale)
     _check(o1[pick].cpu(), ref, "auto")
+
+
+@pytest.mark.parametrize("split", [2, 4])
+@pytest.mark.parametrize("cfg", [  # (heads, kv_heads, head_size, block_size, dtype, kv_dtype)
+    (32, 8, 128, 16, torch.bfloat16, "auto"), (4, 1, 128, 16, torch.bfloat16, "fp8"),
+    (8, 8, 64, 32, torch.float16, "auto"), (16, 2, 256, 16, torch.float16, "fp8_e5m2"),
+    (12, 4, 96, 16, torch.bfloat16, "auto"),
+])
+def test_cluster_split_v1_matches_oracle_and_unsplit(ops, cabi, split, cfg):
+    """v1 with every sequence shared by a thread-block cluster of 2 / 4 CTAs (partials merged in the leader's shared
+    memory through DSMEM): ragged lengths, incl. sequences shorter than the split (CTAs with no block at all), 0 and 1."""
+    nh, nkv, D, BS, dtype, kv_dtype = cfg
+    seq_lens = [0, 1, 15, 17, 33, 700, 1025, 2049]
+    q, kc, vc, bt, sl, _, scale = _mk(len(seq_lens), nh, nkv, D, BS, dtype, kv_dtype, seq_lens)
+    ks, vs = ((0.75, 1.5) if kv_dtype != "auto" else (1.0, 1.0))
+    plain = _run(ops, "v1", q, kc, vc, bt, sl, None, scale, nkv, BS, kv_dtype, ks, vs)
+    assert cabi.b200_last_attention_cluster_split() == 1       # tiny problem: the launcher does not split on its own
+    prev = cabi.b200_set_attention_impl(split)
+    try:
+        out = _run(ops, "v1", q, kc, vc, bt, sl, None, scale, nkv, BS, kv_dtype, ks, vs)
+        assert cabi.b200_last_attention_path() == 1 and cabi.b200_last_attention_cluster_split() == split
+    finally:
+        cabi.b200_set_attention_impl(prev)
+    ref = po.paged_attention(q, kc, vc, bt, sl, scale, None, kv_dtype, ks, vs)
+    assert (out[0] == 0).all()
+    _check(out[1:], ref[1:], kv_dtype)
+    _check(out[1:], plain[1:], kv_dtype)
+
+
+def test_cluster_split_is_chosen_for_under_filled_waves(ops, cabi):
+    """BASELINE configs[3]'s per-GPU shape in small: 1 kv-head, 4 q-heads, enough sequences for a few waves of CTAs but
+    not a multiple of the 2 x SM-count resident set -> the launcher shares each sequence between 2 CTAs by itself."""
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    S = 2 * sms + sms // 2                      # 2.5 waves... of whole-sequence CTAs at 2 per SM: 1.25 waves
+    L = 2048
+    q, kc, vc, bt, sl, _, scale = _mk(S, 4, 1, 128, 16, torch.bfloat16, "fp8", [L] * S, num_blocks=S * (L // 16))
+    out = _run(ops, "v1", q, kc, vc, bt, sl, None, scale, 1, 16, "fp8")
+    assert cabi.b200_last_attention_cluster_split() in (2, 4)
+    idx = [0, S // 2, S - 1]
+    ref = po.paged_attention(q[idx], kc, vc, bt[idx], sl[idx], scale, None, "fp8")
+    _check(out[idx], ref, "fp8")

@@ -81,105 +81,57 @@ def test_random_shapes():
         _check(64 * rng.randint(1, 700), 64 * rng.randint(1, 300), rng.choice([148, 144, 132, 108, 80, 1]))
 
 
-# ---- tcgen05 kernel: whole tiles in full waves + a stream-k tail (csrc/marlin_gemm.cu plan_dense, the kernel's decoding) --
-def _plan_dense(M, N, K, group_size, sms, forced_split=0):
-    """Python restatement of plan_dense -> (full tiles, tail CTAs, chunks per k-unit, k-units per tile, max CTAs per tile)."""
+# ---- tcgen05 kernel: k-split plan (csrc/marlin_gemm.cu plan_split_k + the rounding in b200_gptq_marlin_gemm) ----------
+def _plan_split_k(M, N, K, group_size, sms):
     tiles = ((N + 127) // 128) * ((M + 255) // 256)
     chunks = K // 64
-    unit = group_size // 64 if group_size > 64 else 1
-    if chunks % unit:
-        unit = chunks
-    upt = chunks // unit
-    whole = (tiles, 0, unit, upt, 1)
     if (M + 255) // 256 > 32:
-        return whole
-    if forced_split > 1:
-        full, tail_tiles = 0, tiles
-        units = tiles * upt
-        g = min(tiles * forced_split, units)
-    else:
-        full = tiles // sms * sms
-        tail_tiles = tiles - full
-        units = tail_tiles * upt
-        min_units = max(1, -(-8 // unit))
-        g = min(sms, units // min_units)
-        if tail_tiles == 0 or tail_tiles * 10 >= sms * 9 or g <= tail_tiles:
-            return whole
-    nseg = 1
-    for t in range(tail_tiles):
-        cf = ((t * upt + 1) * g - 1) // units
-        cl = ((t * upt + upt) * g - 1) // units
-        nseg = max(nseg, cl - cf + 1)
-    return (full, g, unit, upt, nseg)
+        return 1
+    split = max(1, min(sms // max(tiles, 1), chunks // 8))
+    gchunks = group_size // 64 if group_size > 64 else 1
+    while split > 1:
+        per = -(-(-(-chunks // split)) // gchunks) * gchunks
+        if (split - 1) * per < chunks:
+            break
+        split -= 1
+    return split
 
 
-def _dense_segments(M, N, K, plan):
-    """What every CTA of the dense launch does: (cta, tile, first chunk, chunk count, CTAs sharing the tile, slab)."""
-    full, g, unit, upt, _ = plan
+def _launch_split(M, N, K, group_size, sms):
+    split = _plan_split_k(M, N, K, group_size, sms)
     tiles = ((N + 127) // 128) * ((M + 255) // 256)
     chunks = K // 64
-    out = [(c, c, 0, chunks, 1, 0) for c in range(full)]
-    if g:
-        units = (tiles - full) * upt
-        for c in range(g):
-            u, u_end = c * units // g, (c + 1) * units // g
-            while u < u_end:
-                tl = u // upt
-                cb = u - tl * upt
-                ce = min(upt, cb + (u_end - u))
-                u += ce - cb
-                cf = ((tl * upt + 1) * g - 1) // units
-                cl = ((tl * upt + upt) * g - 1) // units
-                out.append((full + c, full + tl, cb * unit, (ce - cb) * unit, cl - cf + 1, c - cf))
-    return out
+    while split > 1 and tiles * split > sms:
+        split -= 1
+    while split > 1 and (split - 1) * (-(-chunks // split)) >= chunks:
+        split -= 1
+    gchunks = group_size // 64 if group_size > 64 else 1
+    per = -(-(-(-chunks // split)) // gchunks) * gchunks
+    while split > 1 and (split - 1) * per >= chunks:
+        split -= 1
+        per = -(-(-(-chunks // split)) // gchunks) * gchunks
+    return split, per
 
 
-def _check_dense(M, N, K, gs, sms, forced=0):
-    plan = _plan_dense(M, N, K, gs, sms, forced)
-    full, g, unit, upt, max_nseg = plan
-    tiles = ((N + 127) // 128) * ((M + 255) // 256)
-    chunks = K // 64
-    assert unit * upt == chunks
-    if forced == 0:
-        assert full % sms == 0 or g == 0                                # whole tiles come in complete waves
-    covered = [[0] * chunks for _ in range(tiles)]
-    per_tile, work = {}, {}
-    for cta, tile, c0, n, nseg, slab in _dense_segments(M, N, K, plan):
-        assert n > 0 and c0 + n <= chunks
-        assert gs <= 64 or c0 % (gs // 64) == 0                         # segments start on scale-group boundaries
-        for c in range(c0, c0 + n):
-            covered[tile][c] += 1
-        assert 0 <= slab < nseg <= max_nseg                             # inside the caller's fp32 scratch [plan, M, N]
-        per_tile.setdefault(tile, []).append((cta, slab, nseg))
-        work[cta] = work.get(cta, 0) + n
-    assert all(v == 1 for row in covered for v in row), (M, N, K, gs, plan)
-    for tile, lst in per_tile.items():
-        nseg = lst[0][2]
-        assert all(n == nseg for _, _, n in lst) and len(lst) == nseg   # tickets awaited == CTAs that arrive
-        assert sorted(sl for _, sl, _ in lst) == list(range(nseg))      # slab indices unique and dense
-        assert len({c for c, _, _ in lst}) == nseg                      # one segment per CTA and tile
-    if g:
-        tail = [w for c, w in work.items() if c >= full]
-        assert max(tail) - min(tail) <= unit                            # equal shares of the tail (stream-k)
-    return plan
-
-
-def test_dense_plan_of_the_tcgen05_kernel_covers_every_chunk_once():
+def test_k_split_plan_of_the_tcgen05_kernel():
     rng = random.Random(3)
     shapes = [(256, 6144, 4096, 128), (256, 4096, 4096, 128), (256, 28672, 4096, 128), (256, 4096, 14336, 128),
               (64, 4096, 4096, -1), (200, 64, 64, 32), (4096, 4096, 4096, 128), (9000, 128, 8192, 128)]
-    shapes += [(rng.randint(33, 2000), 64 * rng.randint(1, 300), 64 * rng.randint(1, 200), rng.choice([-1, 32, 64, 128, 256]))
-               for _ in range(200)]
+    shapes += [(rng.randint(33, 2000), 64 * rng.randint(1, 500), 64 * rng.randint(1, 256), rng.choice([-1, 32, 64, 128, 256]))
+               for _ in range(300)]
     for M, N, K, gs in shapes:
         if gs > 0 and K % gs:
             continue
         for sms in (148, 132):
-            _check_dense(M, N, K, gs, sms)
-        _check_dense(M, N, K, gs, 148, forced=rng.randint(2, 5))
-    # the headline case: 224 tiles on 148 SMs -> one full wave of whole tiles + 76 tiles shared by 148 CTAs
-    assert _plan_dense(256, 28672, 4096, 128, 148)[:2] == (148, 148)
-    assert _plan_dense(256, 6144, 4096, 128, 148)[:2] == (0, 148)      # 48 tiles: all of them in the stream-k tail
-    assert _plan_dense(256, 4096 * 37, 4096, 128, 148)[:2] == (1184, 0)   # 1184 = 8 x 148 tiles: nothing to share
+            plan = _plan_split_k(M, N, K, gs, sms)
+            split, per = _launch_split(M, N, K, gs, sms)
+            chunks = K // 64
+            tiles = ((N + 127) // 128) * ((M + 255) // 256)
+            assert 1 <= split <= plan                               # the caller's scratch [plan, M, N] is large enough
+            assert split == 1 or tiles * split <= sms               # one wave of CTAs (the ticket reduce does not need it)
+            assert (split - 1) * per < chunks <= split * per        # all chunks covered, no empty split
+            if gs > 64:
+                assert per % (gs // 64) == 0 or split == 1
 
 
 # ---- grouped (MoE) launch: blockIdx.y -> (expert, tile) over an upper-bound grid ----------------------------------------
@@ -221,9 +173,7 @@ def test_moe_tile_enumeration_covers_every_sorted_row():
 
 
 def test_python_restatement_equals_the_library_plan():
-    """b200_marlin_gemm_plan / b200_marlin_dense_plan run without a GPU (148 SMs assumed): the restatements above are
-    the shipped arithmetic."""
-    import ctypes
+    """b200_marlin_gemm_plan runs without a GPU (148 SMs assumed): the restatements above are the shipped arithmetic."""
     from aphrodite_engine_b200 import _native
     lib = _native.load_c_abi()
     rng = random.Random(11)
@@ -235,11 +185,7 @@ def test_python_restatement_equals_the_library_plan():
         if gs > 0 and K % gs:
             continue
         groups = K // gs if gs > 0 else 1
-        plan = _plan_dense(M, N, K, gs if groups > 1 else -1, 148)
-        expect = plan[4]
+        expect = _plan_split_k(M, N, K, gs if groups > 1 else -1, 148)
         if M <= 32:
             expect = max(expect, small_partition(N, K, 148)[1])
         assert lib.b200_marlin_gemm_plan(M, N, K, groups) == expect, (M, N, K, gs)
-        out = (ctypes.c_int * 5)()
-        assert lib.b200_marlin_dense_plan(M, N, K, groups, out) == 0
-        assert tuple(out) == plan, (M, N, K, gs, tuple(out), plan)

@@ -85,3 +85,30 @@ def test_hqq_marlin_quantize_layout_and_reference_weights(group_size):
     assert torch.equal(mz, om.marlin_permute_scales(zp, K, N, group_size))
     assert torch.equal(ms, om.marlin_permute_scales(s, K, N, group_size))
     assert torch.equal(mq, om.marlin_weights(q.int(), 4))
+
+
+def test_mixtral_quant_dense_per_expert_equals_per_token_routing():
+    """oracle.marlin.mixtral_quant_moe (the reference's dense-per-expert loop, mixtral_quant.py:128-152) against the
+    per-token definition of a top-k MoE in fp32: out[t] = sum_{k: expert(t,k) local} w[t,k] * MLP_e(x[t])."""
+    import torch
+    from oracle import marlin as om
+    torch.manual_seed(0)
+    T, H, I, E, topk = 9, 32, 48, 4, 2
+    x = torch.randn(T, H)
+    gate = torch.randn(E, H)
+    w13 = {e: torch.randn(H, 2 * I) * 0.2 for e in range(E)}
+    w2 = {e: torch.randn(I, H) * 0.2 for e in range(E)}
+    p = torch.softmax(x @ gate.t(), dim=1)
+    w, ids = torch.topk(p, topk, dim=-1)
+    w = w / w.sum(-1, keepdim=True)
+    for local in ([0, 1, 2, 3], [2, 3], [1]):
+        got = om.mixtral_quant_moe(x, gate, w13, w2, topk, local)
+        want = torch.zeros(T, H)
+        for t in range(T):
+            for k in range(topk):
+                e = int(ids[t, k])
+                if e in local:
+                    gu = x[t] @ w13[e]
+                    h = torch.nn.functional.silu(gu[:I]) * gu[I:]
+                    want[t] += w[t, k] * (h @ w2[e])
+        torch.testing.assert_close(got, want, atol=1e-4, rtol=1e-4)
