@@ -586,51 +586,42 @@ marlin_w4a16_tc5_kernel(const __grid_constant__ CUtensorMap tmap_a, const Marlin
         }
       }
     }
-    if (slab != nullptr) {
-      // split-k: every split has stored its fp32 partial in its own slab; the LAST split to arrive (atomic ticket on
-      // the tile's lock in the reference's zeroed `workspace`) sums the slabs in split order — deterministic, no atomics
-      // on data, no spinning and therefore no co-residency requirement between the splits of a tile (they may run in
-      // different waves, or beside other kernels; round 1 had every split spin until all had arrived) — writes C and
-      // returns the lock to zero (kernels/torch_bindings.cpp:167-176 contract).
-      constexpr int EPI = MG_DQ_WARPS * 32;
-      __shared__ int s_last;
-      const int tile = blockIdx.y * gridDim.x + blockIdx.x;
-      int* lock = p.locks + tile;
-      __threadfence();                                           // this thread's slab stores before the ticket
-      asm volatile("bar.sync 1, %0;" ::"n"(EPI) : "memory");
-      if (threadIdx.x == 0) {
-        const int t = atomicAdd(lock, 1);
-        s_last = (t == p.split_k - 1);
-        if (s_last) atomicExch(lock, 0);
-      }
-      asm volatile("bar.sync 1, %0;" ::"n"(EPI) : "memory");
-      if (s_last) {
-        __threadfence();                                         // the other splits' slabs (published before their tickets)
-        const int nvalid = min(MG_NT, p.N - n_base);             // channels of this tile (64 or 128)
-        if (lane * 4 < nvalid) {
-          for (int r = warp; r < toks; r += MG_DQ_WARPS) {
-            const size_t off = (size_t)(tok_base + r) * p.N + n_base + lane * 4;
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int z0 = 0; z0 < p.split_k; z0 += 4) {            // four slab loads in flight, added in split order
-              float4 v[4];
+    if (prof && warp == 0 && lane == 0) g_mg_prof[15] = (unsigned long long)(clock64() - t_role0);
+    tc_fence_before();
+  }
+  if (!MOE && p.split_k > 1) {
+    // split-k: the splits of a tile are the CTAs of one thread-block CLUSTER (1, 1, split_k), so the hardware
+    // guarantees that they are co-resident and `barrier.cluster` is a rendezvous that cannot deadlock, whatever else
+    // runs on the GPU (round 1 spun on a lock in global memory and relied on the whole grid being resident). Every
+    // split has stored its fp32 partial in its own slab; after the barrier EACH split reduces an interleaved
+    // 1 / split_k share of the token rows over the slabs in split order: deterministic, no atomics, no second kernel,
+    // and the reduction is spread over split_k SMs. The lock workspace of the reference's contract is not touched.
+    __threadfence();                                            // slab stores -> visible to the cluster's other SMs
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (warp < MG_DQ_WARPS && nchunks > 0) {
+      T* cptr = reinterpret_cast<T*>(p.c);
+      const int nvalid = min(MG_NT, p.N - n_base);              // channels of this tile (64 or 128)
+      if (lane * 4 < nvalid) {
+        for (int r = blockIdx.z + p.split_k * warp; r < toks; r += p.split_k * MG_DQ_WARPS) {
+          const size_t off = (size_t)(tok_base + r) * p.N + n_base + lane * 4;
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int z0 = 0; z0 < p.split_k; z0 += 4) {           // four slab loads in flight, added in split order
+            float4 v[4];
 #pragma unroll
-              for (int z = 0; z < 4; ++z)
-                v[z] = (z0 + z < p.split_k)
-                           ? __ldcg(reinterpret_cast<const float4*>(p.c_tmp + (size_t)(z0 + z) * p.M * p.N + off))
-                           : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int z = 0; z < 4; ++z)
+              v[z] = (z0 + z < p.split_k)
+                         ? __ldcg(reinterpret_cast<const float4*>(p.c_tmp + (size_t)(z0 + z) * p.M * p.N + off))
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-              for (int z = 0; z < 4; ++z) { acc.x += v[z].x; acc.y += v[z].y; acc.z += v[z].z; acc.w += v[z].w; }
-            }
-            uint2 o;
-            o.x = pack2<T>(acc.x, acc.y);
-            o.y = pack2<T>(acc.z, acc.w);
-            *reinterpret_cast<uint2*>(cptr + off) = o;
+            for (int z = 0; z < 4; ++z) { acc.x += v[z].x; acc.y += v[z].y; acc.z += v[z].z; acc.w += v[z].w; }
           }
+          uint2 o;
+          o.x = pack2<T>(acc.x, acc.y);
+          o.y = pack2<T>(acc.z, acc.w);
+          *reinterpret_cast<uint2*>(cptr + off) = o;
         }
       }
     }
-    if (prof && warp == 0 && lane == 0) g_mg_prof[15] = (unsigned long long)(clock64() - t_role0);
-    tc_fence_before();
   }
   __syncthreads();
   if (warp == MG_WARP_TMA) {
@@ -712,7 +703,7 @@ static int plan_split_k(int M, int N, int K, int group_size) {
   if ((M + MG_TOK - 1) / MG_TOK > 32) return 1;   // lock workspace (N/64*16 ints) covers <= 32 token blocks
   // as many k-splits as fit one wave of the SMs (one CTA per SM) with at least 8 chunks each: 48 tiles -> 3 splits =
   // 144 CTAs (a power-of-two rule left a third of the SMs idle)
-  int split = std::min(sms / std::max(tiles, 1), chunks / 8);
+  int split = std::min(std::min(sms / std::max(tiles, 1), chunks / 8), 8);   // 8 = portable cluster size
   if (split < 1) split = 1;
   // keep every split on a group boundary and none empty
   const int gchunks = group_size > MG_KC ? group_size / MG_KC : 1;
@@ -741,8 +732,54 @@ static int launch_marlin_v(const CUtensorMap& tmap, MarlinParams& p, dim3 grid, 
   if (p.stages > MG_MAX_STAGES) p.stages = MG_MAX_STAGES;
   B200_CHECK(p.stages >= 2, "marlin gemm: shared-memory plan leaves fewer than two pipeline stages");
   const size_t smem = (size_t)p.stages * (p.act_bytes + MG_W_BYTES) + FIXED;
-  kern<<<grid, MG_THREADS, smem, st>>>(tmap, p);
+  if (!MOE && p.split_k > 1) {
+    // the k-splits of a tile form one cluster (1, 1, split_k): co-residency guaranteed by the hardware
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(MG_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = (unsigned)p.split_k;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    B200_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmap, p));
+  } else {
+    kern<<<grid, MG_THREADS, smem, st>>>(tmap, p);
+  }
   return check_launch("marlin_w4a16_tc5_kernel");
+}
+
+// how many clusters of `split` CTAs of this kernel the device can hold at once (the k-splits of a tile must not be
+// queued behind other tiles' clusters, or the split costs a second wave); all instantiations share the launch shape
+static int max_active_clusters(int split) {
+  static thread_local int cache[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  if (split < 2 || split > 8) return 1 << 30;
+  if (cache[split] == 0) {
+    auto kern = marlin_w4a16_tc5_kernel<__nv_bfloat16, ZP_NONE, 4, false, false>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_SMEM_TOTAL);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(1, 1, (unsigned)split);
+    cfg.blockDim = dim3(MG_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = MG_SMEM_TOTAL - 1024;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = (unsigned)split;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) {
+      cudaGetLastError();
+      n = num_sms() / split;      // no device (plan queries on a CPU box) or no answer: the arithmetic bound
+    }
+    cache[split] = n;
+  }
+  return cache[split];
 }
 
 // weight-operand path: register prefetch by default (one more pipeline stage at 256 tokens: 794 vs 762 TFLOP/s
@@ -889,7 +926,8 @@ extern "C" int b200_gptq_marlin_gemm(const void* a, const void* b_q_weight, cons
              "split-k needs the fp32 partial buffer [split_k, M, N] and the zeroed lock workspace");
   {
     const int tiles = ((size_n + MG_NT - 1) / MG_NT) * ((size_m + MG_TOK - 1) / MG_TOK);
-    while (split_k > 1 && tiles * split_k > num_sms()) --split_k;   // one wave
+    while (split_k > 1 && (tiles * split_k > num_sms() || tiles > max_active_clusters(split_k))) --split_k;   // one wave
+    if (split_k > 8) split_k = 8;
     const int chunks_total = size_k / MG_KC;
     while (split_k > 1 && (split_k - 1) * ((chunks_total + split_k - 1) / split_k) >= chunks_total) --split_k;
   }

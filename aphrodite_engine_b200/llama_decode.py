@@ -225,7 +225,15 @@ class LlamaDecoder:
             else:
                 fullkv = torch.empty(2, num_blocks, s.kv_heads, per_head, dtype=store, device=dev)
                 if store == torch.uint8:
-                    fullkv.random_(0, 120, generator=g)
+                    # fp8 cache = convert_fp8 of a U(-s, s) 16-bit cache, as the reference's benchmarks fill theirs
+                    # (aphrodite/common/utils.py:604-621), in slabs of blocks to bound the 16-bit temporary
+                    step = max(1, (1 << 28) // (s.kv_heads * per_head))
+                    for plane in range(2):
+                        for b0 in range(0, num_blocks, step):
+                            dst = fullkv[plane, b0:b0 + step]
+                            src = torch.empty(dst.shape, dtype=self.dtype, device=dev).uniform_(-self.scale, self.scale,
+                                                                                               generator=g)
+                            ops.convert_fp8(dst, src, 1.0, self.kv_cache_dtype)
                 else:
                     fullkv.uniform_(-self.scale, self.scale, generator=g)
                 if self.tp_size > 1:

@@ -43,6 +43,11 @@ def _graph_of(env, fn, ca=None):
         return None
 
 
+def _native_split():
+    from aphrodite_engine_b200 import _native
+    return int(_native.load_c_abi().b200_last_attention_cluster_split())
+
+
 def _ref_table():
     from oracle import ref_cuda_ops as rco
     if not rco.available():
@@ -163,9 +168,13 @@ def cfg4_fp8kv(env, args, model, shape, dtype, peaks):
         nb = B * nb_per
         g = torch.Generator(device=env.dev).manual_seed(7)
         caches = []
+        import aphrodite_engine_b200._custom_ops as ops
         for _ in range(2):
             kv = torch.empty(PagedAttention.get_kv_cache_shape(nb, BS, kvh, D), dtype=torch.uint8, device=env.dev)
-            kv.random_(0, 120, generator=g)
+            for plane in range(2):          # fp8 cache = convert_fp8 of U(-s, s), like the reference's benchmark caches
+                src = torch.empty(kv[plane].shape, dtype=dtype, device=env.dev).uniform_(-D ** -0.5, D ** -0.5, generator=g)
+                ops.convert_fp8(kv[plane], src, 1.0, "fp8")
+                del src
             caches.append(PagedAttention.split_kv_cache(kv, kvh, D))
         bt = torch.randperm(nb, device=env.dev, generator=g).view(B, nb_per).to(torch.int32)
         sl = torch.full((B,), CTX, dtype=torch.int32, device=env.dev)
@@ -183,8 +192,10 @@ def cfg4_fp8kv(env, args, model, shape, dtype, peaks):
             idx = [0, B // 2, B - 1]
             ref = po.paged_attention(q[idx].cpu(), kc.cpu(), vc.cpu(), bt[idx].cpu(), sl[idx].cpu(), D ** -0.5,
                                      kv_cache_dtype="fp8")
-            err = float((o[idx].float().cpu() - ref.float()).abs().max())
-            out["parity"] = {"max_abs_err_vs_oracle_on_3_sequences": err, "ok": err <= 2e-3 + 2e-3 * float(ref.float().abs().max())}
+            err = (o[idx].float().cpu() - ref.float()).abs()
+            ok = bool((err <= 2e-3 + 1e-3 * ref.float().abs()).all())      # tests/tolerances.py: fp8 KV atol 2e-3, rtol 1e-3
+            out["parity"] = {"max_abs_err_vs_oracle_on_3_sequences": float(err.max()), "ok": ok,
+                             "cluster_split": _native_split()}
         del caches
     algo_bytes = B * CTX * 2 * kvh * shape.head_size * 1 + 2 * B * heads * shape.head_size * 2 + B * (CTX // BS) * 4
     ach = algo_bytes / (attn_ms * 1e-3) / 1e9
@@ -245,13 +256,16 @@ def cfg5_mixtral_moe(env, args, model, dtype, peaks):
             par["ok"] = env.all_agree(exact)
         out["parity"] = par
     H, I, G = ms_shape.hidden, ms_shape.intermediate, ms_shape.group_size
+    n_local = len(layers[0].experts)
     per_expert = (H * 2 * I + I * H) // 2 + ((H // G) * 2 * I + (I // G) * H) * 2 + ((H // G) * 2 * I + (I // G) * H) // 2
-    algo = per_expert * len(layers[0].experts)
-    ach = algo / (ms * 1e-3) / 1e9
-    out["roofline"] = {"kernel": "marlin_w4a16_tc5_kernel (AWQ zero points, M=128) per MoE block", "bound": "hbm",
-                       "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
-                       "algorithmic_bytes_per_layer": algo,
-                       "note": "bytes = packed expert weights + scales + zero points of the local experts (each read once)"}
+    flops = 2.0 * T * (H * 2 * I + I * H) * n_local
+    peak_tf = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0))
+    tf = flops / (ms * 1e-3) / 1e12
+    # dense per expert at 128 tokens: 512 flop per packed-weight byte, above the ~220 flop/B ridge -> tensor-bound
+    out["roofline"] = {"kernel": "marlin_w4a16_tc5_kernel (AWQ zero points, M=128), whole MoE block", "bound": "tensor",
+                       "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf,
+                       "flops_per_layer": flops, "weight_bytes_per_layer": per_expert * n_local,
+                       "weight_GBps": per_expert * n_local / (ms * 1e-3) / 1e9}
     del layers
     torch.cuda.empty_cache()
     return out

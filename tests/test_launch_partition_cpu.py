@@ -87,7 +87,7 @@ def _plan_split_k(M, N, K, group_size, sms):
     chunks = K // 64
     if (M + 255) // 256 > 32:
         return 1
-    split = max(1, min(sms // max(tiles, 1), chunks // 8))
+    split = max(1, min(sms // max(tiles, 1), chunks // 8, 8))
     gchunks = group_size // 64 if group_size > 64 else 1
     while split > 1:
         per = -(-(-(-chunks // split)) // gchunks) * gchunks
@@ -128,7 +128,7 @@ def test_k_split_plan_of_the_tcgen05_kernel():
             chunks = K // 64
             tiles = ((N + 127) // 128) * ((M + 255) // 256)
             assert 1 <= split <= plan                               # the caller's scratch [plan, M, N] is large enough
-            assert split == 1 or tiles * split <= sms               # one wave of CTAs (the ticket reduce does not need it)
+            assert split == 1 or (tiles * split <= sms and split <= 8)   # one wave of clusters of <= 8 CTAs
             assert (split - 1) * per < chunks <= split * per        # all chunks covered, no empty split
             if gs > 64:
                 assert per % (gs // 64) == 0 or split == 1
