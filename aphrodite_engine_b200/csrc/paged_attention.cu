@@ -734,18 +734,20 @@ static int launch_tc(const AttnParams& p, cudaStream_t st) {
   dim3 grid(p.num_kv_heads * groups, p.num_seqs, PART ? p.max_num_partitions : 1);
   int cs = 1;
   if constexpr (!PART) {
-    // split every sequence over a cluster of cs CTAs when that fills the waves of 2 CTAs per SM visibly better
-    // (and every CTA still streams >= 64 blocks); g_force_impl 2 / 4 force a split (tests)
+    // split every sequence over a cluster of cs CTAs when the launch would otherwise leave SM slots empty (fewer
+    // CTAs than the 2-per-SM resident set: small batches / few kv-heads per GPU) and every CTA still streams >= 64
+    // blocks. A grid of more than one wave is NOT split: the kernel is HBM-bound and a partially filled last wave still
+    // saturates the memory system (measured: 1024 CTAs at 0.99-1.04 of the HBM peak unsplit, 0.99 split).
+    // g_force_impl 2 / 4 force a split (tests)
     const long long n = (long long)grid.x * grid.y, resident = 2LL * num_sms();
     const int max_blocks = p.max_seq_len > 0 ? std::min((p.max_seq_len + BS - 1) / BS, p.max_num_blocks_per_seq)
                                              : p.max_num_blocks_per_seq;
-    auto eff = [&](int c) { const long long m = n * c; return (double)m / (double)(((m + resident - 1) / resident) * resident); };
     auto fits = [&](int c) { return Cfg::MERGE_BYTES + c * kHeadsPerCta * Cfg::OPAD * 4 <= Cfg::DATA_BYTES; };
     if (g_force_impl == 2 || g_force_impl == 4) {
       cs = fits(g_force_impl) ? g_force_impl : 1;
     } else {
       for (int c = 2; c <= kMaxClusterSplit; c *= 2)
-        if (fits(c) && max_blocks / c >= 64 && eff(c) > eff(cs) + 0.04) cs = c;
+        if (fits(c) && max_blocks / c >= 64 && n * c <= resident) cs = c;
     }
   }
   if (cs == 1) {

@@ -136,28 +136,39 @@ __device__ __forceinline__ uint4 ld_peer_v4(const void* a) {
   return v;
 }
 
-template <typename T, int ALGO>
-__device__ __forceinline__ uint4 tp_reduce_packet(const TpParams& p, int64_t byte_off) {
+// The VPT packets of one thread: every load of every packet is issued before the first add, so a row costs ONE
+// NVLink round trip whatever VPT and the world size are.
+template <typename T, int ALGO, int VPT>
+__device__ __forceinline__ void tp_reduce_packets(const TpParams& p, int64_t row_off, int nvec, Pk<T> (&z)[VPT]) {
   if constexpr (ALGO == TP_MC_REDUCE) {
-    return mc_ld_reduce<T>(p.mc_base + p.in_off + byte_off);
-  } else {
-  float acc[Pk<T>::N];
 #pragma unroll
-  for (int e = 0; e < Pk<T>::N; ++e) acc[e] = 0.f;
-  Pk<T> v[kTpMaxRanks];
-#pragma unroll
-  for (int r = 0; r < kTpMaxRanks; ++r)   // all peer loads in flight before the first add
-    if (r < p.world) v[r].raw = ld_peer_v4(p.peer_base[r] + p.in_off + byte_off);
-#pragma unroll
-  for (int r = 0; r < kTpMaxRanks; ++r)
-    if (r < p.world) {
-#pragma unroll
-      for (int e = 0; e < Pk<T>::N; ++e) acc[e] += to_f32<T>(v[r].e[e]);
+    for (int k = 0; k < VPT; ++k) {
+      const int v = threadIdx.x + k * kTpThreads;
+      if (v < nvec) z[k].raw = mc_ld_reduce<T>(p.mc_base + p.in_off + row_off + (int64_t)v * 16);
     }
-  Pk<T> o;
+  } else {
+    Pk<T> in[VPT][kTpMaxRanks];
 #pragma unroll
-  for (int e = 0; e < Pk<T>::N; ++e) o.e[e] = from_f32<T>(acc[e]);
-  return o.raw;
+    for (int k = 0; k < VPT; ++k) {
+      const int v = threadIdx.x + k * kTpThreads;
+#pragma unroll
+      for (int r = 0; r < kTpMaxRanks; ++r)
+        if (r < p.world && v < nvec) in[k][r].raw = ld_peer_v4(p.peer_base[r] + p.in_off + row_off + (int64_t)v * 16);
+    }
+#pragma unroll
+    for (int k = 0; k < VPT; ++k) {
+      float acc[Pk<T>::N];
+#pragma unroll
+      for (int e = 0; e < Pk<T>::N; ++e) acc[e] = 0.f;
+#pragma unroll
+      for (int r = 0; r < kTpMaxRanks; ++r)          // rank order, fp32: the reference kernel's arithmetic
+        if (r < p.world) {
+#pragma unroll
+          for (int e = 0; e < Pk<T>::N; ++e) acc[e] += to_f32<T>(in[k][r].e[e]);
+        }
+#pragma unroll
+      for (int e = 0; e < Pk<T>::N; ++e) z[k].e[e] = from_f32<T>(acc[e]);
+    }
   }
 }
 template <int ALGO>
@@ -184,21 +195,28 @@ __global__ void __launch_bounds__(kTpThreads) tp_allreduce_rows_kernel(const TpP
   const uint32_t t_start = (2u * epoch + 1u) * (uint32_t)p.world;
   const uint32_t t_end = (2u * epoch + 2u) * (uint32_t)p.world;
 
-  tp_signal<ALGO, false>(p, blockIdx.x);
-  tp_wait(p, blockIdx.x, t_start);
-
   const int rows_per = (p.num_tokens + p.world - 1) / p.world;
   const int row0 = p.rank * rows_per;
   const int row1 = min(p.num_tokens, row0 + rows_per);
   const int nvec = p.hidden / N;
   const int64_t row_bytes = (int64_t)p.hidden * sizeof(T);
-  for (int row = row0 + blockIdx.x; row < row1; row += gridDim.x) {
-    Pk<T> z[VPT];
+
+  tp_signal<ALGO, false>(p, blockIdx.x);
+  // the first row's residual does not depend on the peers: fetch it while the start barrier is in flight
+  Pk<T> rpre[VPT];
+  if (NORM && row0 + (int)blockIdx.x < row1) {
+    const T* res = reinterpret_cast<const T*>(p.residual) + (int64_t)(row0 + blockIdx.x) * p.hidden;
 #pragma unroll
     for (int k = 0; k < VPT; ++k) {
       const int v = threadIdx.x + k * kTpThreads;
-      if (v < nvec) z[k].raw = tp_reduce_packet<T, ALGO>(p, row * row_bytes + (int64_t)v * 16);
+      if (v < nvec) rpre[k].raw = *reinterpret_cast<const uint4*>(res + (int64_t)v * N);
     }
+  }
+  tp_wait(p, blockIdx.x, t_start);
+
+  for (int row = row0 + blockIdx.x; row < row1; row += gridDim.x) {
+    Pk<T> z[VPT];
+    tp_reduce_packets<T, ALGO, VPT>(p, row * row_bytes, nvec, z);
     if (NORM) {
       float ss = 0.f;
       T* res = reinterpret_cast<T*>(p.residual) + (int64_t)row * p.hidden;
@@ -207,7 +225,8 @@ __global__ void __launch_bounds__(kTpThreads) tp_allreduce_rows_kernel(const TpP
         const int v = threadIdx.x + k * kTpThreads;
         if (v < nvec) {
           Pk<T> r;
-          r.raw = *reinterpret_cast<const uint4*>(res + (int64_t)v * N);
+          if (row == row0 + (int)blockIdx.x) r.raw = rpre[k].raw;
+          else r.raw = *reinterpret_cast<const uint4*>(res + (int64_t)v * N);
 #pragma unroll
           for (int e = 0; e < N; ++e) {
             z[k].e[e] = from_f32<T>(__fadd_rn(to_f32<T>(z[k].e[e]), to_f32<T>(r.e[e])));

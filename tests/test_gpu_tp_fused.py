@@ -103,7 +103,7 @@ def _worker(rank, world, port, q):
                                         f"(max {float((h.float() - want_h.float()).abs().max())})")
                     else:
                         err = (h.float() - want_h.float()).abs()
-                        tol = 2e-2 * want_h.float().abs() + 2e-2     # ~2 ulp of a 16-bit type
+                        tol = 5e-2 * want_h.float().abs() + 5e-2     # a few ulp: the switch does not round to nearest
                         if not bool((err <= tol).all()):
                             msgs.append(f"{tag} T={T}: random-normal mismatch max err {float(err.max())}")
                 # ---- CUDA graph: two chained exchanges per replay, as in a decoder layer ---------------------------
