@@ -681,6 +681,7 @@ def ref_cuda_leg(env, args, model, st, shape, num_blocks, dtype, ms_mine, K):
             ar = "reference custom_all_reduce kernel"
         else:
             ref_ca = None
+    env.ref_ca, env.ref_ar = ref_ca, ar          # the secondary legs' reference arms reuse it
     ref_model = LlamaDecoder(shape, args.batch, args.block_size, num_blocks, env.dev, dtype, args.kv_cache_dtype,
                              tp_rank=env.rank, tp_size=env.world, group=env.group, quant=args.quant,
                              custom_ar=ref_ca, op_table=table, attention_cls=rco.make_attention_cls(table),

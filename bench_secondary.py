@@ -77,16 +77,17 @@ def cfg3_gptq_step(env, args, model, st, shape, num_blocks, dtype, peaks):
         # the same step over the reference's Marlin kernel (and its other kernels), same weights
         table, attn_cls = _ref_table()
         if table is not None:
+            ref_ca = getattr(env, "ref_ca", None)    # the reference's own custom all-reduce (fp32 rank-order sum), if set up
             r = LlamaDecoder(shape, args.batch, args.block_size, num_blocks, env.dev, dtype, args.kv_cache_dtype,
                              tp_rank=env.rank, tp_size=env.world, group=env.group, quant="gptq", op_table=table,
-                             attention_cls=attn_cls, share_from=q)
+                             attention_cls=attn_cls, custom_ar=ref_ca, share_from=q)
             for _ in range(2):
                 r.forward(st)
             rel = float((h_mine - r.last_hidden.float()).norm() / r.last_hidden.float().norm().clamp_min(1e-30))
-            gr = _graph_of(env, lambda: r.forward(st))
+            gr = _graph_of(env, lambda: r.forward(st), ref_ca)
             ms_r = _time(env, (gr.replay if gr is not None else (lambda: r.forward(st))), 5, 2 if env.world == 1 else 6)
             out["ref_cuda"] = {"ms_per_step": ms_r, "value": args.batch / (ms_r * 1e-3), "ratio": ms_r / ms,
-                               "allreduce": "nccl" if env.world > 1 else "none",
+                               "allreduce": getattr(env, "ref_ar", "nccl") if env.world > 1 else "none",
                                "hidden_rel_fro_err_vs_this_repo": rel, "parity_ok": env.all_agree(rel <= 3e-2)}
             del r, gr
         # the four projection GEMMs alone (tensor-bound at M = 256): TFLOP/s against the measured bf16 tensor peak
