@@ -91,8 +91,12 @@ def test_custom_all_reduce_matches_nccl(world):
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=240) for _ in range(world)]
-    for p in procs:
-        p.join(timeout=30)
+    try:
+        res = [q.get(timeout=150) for _ in range(world)]
+    finally:                      # never leave a rank spinning on a GPU behind a failed or timed-out run
+        for p in procs:
+            p.join(timeout=20)
+            if p.is_alive():
+                p.kill()
     for rank, ok, msgs in res:
         assert ok, f"rank {rank}: {msgs}"

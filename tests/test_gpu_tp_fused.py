@@ -160,9 +160,13 @@ def test_tp_fused_exchange_matches_nccl_plus_norm(world):
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=150) for _ in range(world)]
-    for p in procs:
-        p.join(timeout=30)
+    try:
+        res = [q.get(timeout=150) for _ in range(world)]
+    finally:                      # never leave a rank spinning on a GPU behind a failed or timed-out run
+        for p in procs:
+            p.join(timeout=20)
+            if p.is_alive():
+                p.kill()
     for rank, ok, msgs, info in res:
         print(f"rank {rank}: {info} {msgs}")
         assert ok, f"rank {rank}: {msgs}"
