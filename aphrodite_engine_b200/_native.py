@@ -69,6 +69,7 @@ SIGNATURES = {
     "b200_car_get_graph_buffer_ipc_meta": [c_int64, c_void_p, c_void_p, c_int],
     "b200_car_register_graph_buffers": [c_int64, c_void_p, c_void_p, c_int],
     "b200_tp_flag_bytes": [],
+    "b200_tp_set_stamp_buffer": [c_void_p],
     "b200_tp_allreduce_rows": [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p,
                                c_float] + [c_int] * 6 + [c_void_p],
     "b200_get_device_attribute": [c_int64, c_int64],
@@ -76,6 +77,7 @@ SIGNATURES = {
 }
 _RESTYPES = {
     "b200_tp_flag_bytes": c_int64,
+    "b200_tp_set_stamp_buffer": None,
     "b200_car_meta_size": c_int64,
     "b200_car_init": c_int64,
     "b200_car_dispose": None,

@@ -54,7 +54,14 @@ struct TpParams {
   const void* weight;                // [H] (NORM only)
   float eps;
   int num_tokens, hidden, rank, world;
+  unsigned long long* stamps;        // optional [5] globaltimer stamps of CTA 0 (bring-up / profiling), else nullptr
 };
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 // flag area: u32 counter[kTpMaxBlocks] (signalled by every rank, twice per launch) | u32 epoch[kTpMaxBlocks] (local)
 __device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
@@ -201,6 +208,8 @@ __global__ void __launch_bounds__(kTpThreads) tp_allreduce_rows_kernel(const TpP
   const int nvec = p.hidden / N;
   const int64_t row_bytes = (int64_t)p.hidden * sizeof(T);
 
+  const bool stamp = p.stamps != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+  if (stamp) p.stamps[0] = globaltimer_ns();
   tp_signal<ALGO, false>(p, blockIdx.x);
   // the first row's residual does not depend on the peers: fetch it while the start barrier is in flight
   Pk<T> rpre[VPT];
@@ -213,10 +222,12 @@ __global__ void __launch_bounds__(kTpThreads) tp_allreduce_rows_kernel(const TpP
     }
   }
   tp_wait(p, blockIdx.x, t_start);
+  if (stamp) p.stamps[1] = globaltimer_ns();
 
   for (int row = row0 + blockIdx.x; row < row1; row += gridDim.x) {
     Pk<T> z[VPT];
     tp_reduce_packets<T, ALGO, VPT>(p, row * row_bytes, nvec, z);
+    if (stamp && row == row0) p.stamps[2] = globaltimer_ns() + 0 * (unsigned long long)z[0].raw.x;   // after the loads landed
     if (NORM) {
       float ss = 0.f;
       T* res = reinterpret_cast<T*>(p.residual) + (int64_t)row * p.hidden;
@@ -264,8 +275,10 @@ __global__ void __launch_bounds__(kTpThreads) tp_allreduce_rows_kernel(const TpP
     }
   }
   __syncthreads();                 // every thread's stores happen-before the release-add of the signalling thread(s)
+  if (stamp) p.stamps[3] = globaltimer_ns();
   tp_signal<ALGO, true>(p, blockIdx.x);
   tp_wait(p, blockIdx.x, t_end);
+  if (stamp) p.stamps[4] = globaltimer_ns();
   if (threadIdx.x == 0) flags[kTpMaxBlocks + blockIdx.x] = epoch + 1u;
 }
 
@@ -286,6 +299,11 @@ static int launch_tp(const TpParams& p, cudaStream_t st) {
 }  // namespace b200
 
 using namespace b200;
+
+static thread_local unsigned long long* g_tp_stamps = nullptr;
+// profiling hook: device buffer of 5 x u64 that CTA 0 of the following launches fills with %globaltimer stamps
+// (kernel start, start barrier passed, first row's loads landed, stores issued, end barrier passed); nullptr = off
+extern "C" void b200_tp_set_stamp_buffer(void* dev_u64x5) { g_tp_stamps = static_cast<unsigned long long*>(dev_u64x5); }
 
 extern "C" int64_t b200_tp_flag_bytes(void) { return (int64_t)(2 * kTpMaxBlocks * sizeof(uint32_t)); }
 
@@ -315,6 +333,7 @@ extern "C" int b200_tp_allreduce_rows(void* mc_base, void* local_base, const int
   p.in_off = in_off; p.out_off = out_off; p.flag_off = flag_off;
   p.residual = residual; p.weight = weight; p.eps = epsilon;
   p.num_tokens = num_tokens; p.hidden = hidden; p.rank = rank; p.world = world;
+  p.stamps = g_tp_stamps;
   cudaStream_t st = (cudaStream_t)stream;
   const bool norm = residual != nullptr;
 #define B200_TP_A(T, A) (norm ? launch_tp<T, A, true>(p, st) : launch_tp<T, A, false>(p, st))

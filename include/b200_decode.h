@@ -276,6 +276,10 @@ int b200_car_register_graph_buffers(int64_t fa, const void* handles, const int64
  * not round-to-nearest-even, so results are NOT bit-identical to the reference: opt-in). */
 enum { B200_TP_P2P = 0, B200_TP_MC_STORE = 1, B200_TP_MC_REDUCE = 2 };
 int64_t b200_tp_flag_bytes(void);
+/* profiling hook: CTA 0 of the following b200_tp_allreduce_rows launches (this host thread) writes 5 %globaltimer
+ * stamps (ns) into the device buffer: kernel start, start barrier passed, first row's loads landed, stores issued,
+ * end barrier passed. NULL switches it off. */
+void b200_tp_set_stamp_buffer(void* dev_u64x5);
 int b200_tp_allreduce_rows(void* mc_base, void* local_base, const int64_t* peer_bases, int64_t in_off,
                            int64_t out_off, int64_t flag_off, void* residual, const void* weight,
                            float epsilon, int num_tokens, int hidden, int rank, int world, int dtype,

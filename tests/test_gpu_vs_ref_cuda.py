@@ -350,3 +350,24 @@ def test_misc_ops_vs_reference_kernel(ops, ref):
     torch.cuda.synchronize()
     for x, y in zip(*st):
         assert torch.equal(x, y)
+
+
+@pytest.mark.parametrize("kn", [(4096, 1536), (1024, 4096), (4096, 7168), (3584, 4096),      # Llama-3-8B linears at TP=4
+                                (4096, 768), (512, 4096), (4096, 3584), (1792, 4096),       # ... at TP=8
+                                (2048, 4096), (7168, 4096), (4096, 3072), (4096, 14336)])   # ... at TP=2
+@pytest.mark.parametrize("M", [256, 64])
+def test_marlin_tp_shard_shapes_vs_reference_kernel(ops, ref, kn, M):
+    """The shapes a tensor-parallel GPTQ decode step launches (bench_secondary cfg3 at N = 2 / 4 / 8), with random
+    packed words and scales as the benchmark's dummy weights have them: this repo's kernel against the reference's."""
+    K, N = kn
+    g = torch.Generator(device=DEV).manual_seed(K + N + M)
+    a = (torch.randn(M, K, generator=g, device=DEV) * 0.5).to(torch.bfloat16)
+    q = torch.randint(-2**31, 2**31 - 1, (K // 16, N * 2), generator=g, device=DEV, dtype=torch.int32)
+    s = (torch.rand(K // 128, N, generator=g, device=DEV) * 0.004 + 0.001).to(torch.bfloat16)
+    empty = torch.empty(0, dtype=torch.int32, device=DEV)
+    ws = lambda: torch.zeros((N // 64) * 16, dtype=torch.int32, device=DEV)
+    st = _types().uint4b8
+    mine = ops.gptq_marlin_gemm(a, q, s, empty, empty, empty, ws(), st, M, N, K, True, False, True, False)
+    theirs = _ref_gemm(ref, a, q, s, empty, empty, empty, ws(), st, M, N, K, False)
+    torch.cuda.synchronize()
+    _close(mine, theirs)

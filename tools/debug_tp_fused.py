@@ -67,6 +67,20 @@ for algo in ("mc_store", "mc_reduce", "p2p"):
     for _ in range(200): tp.allreduce_add_rms_norm(T, res, w, 1e-5)
     e1.record(); torch.cuda.synchronize()
     say(f"eager fused: {e0.elapsed_time(e1) / 200 * 1e3:.2f} us/call")
+    # where the time goes inside one call: %globaltimer stamps of CTA 0 (median over 30 eager calls)
+    from aphrodite_engine_b200 import _native
+    lib = _native.load_c_abi()
+    stamps = torch.zeros(5, dtype=torch.int64, device=dev)
+    lib.b200_tp_set_stamp_buffer(stamps.data_ptr())
+    rows = []
+    for _ in range(30):
+        tp.allreduce_add_rms_norm(T, res, w, 1e-5)
+        torch.cuda.synchronize()
+        v = stamps.tolist()
+        rows.append([v[i + 1] - v[i] for i in range(4)])
+    lib.b200_tp_set_stamp_buffer(None)
+    med = [sorted(r[i] for r in rows)[len(rows) // 2] for i in range(4)]
+    say(f"{algo} phases (ns, median): start-barrier {med[0]}, loads {med[1]}, norm+stores-issued {med[2]}, end-barrier {med[3]}")
     g = torch.cuda.CUDAGraph()
     s = torch.cuda.Stream()
     with torch.cuda.stream(s):
