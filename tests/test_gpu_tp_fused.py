@@ -45,7 +45,7 @@ def _worker(rank, world, port, q):
                 acc += part.float()
             return acc.to(x.dtype)
 
-        for dtype in (torch.bfloat16, torch.float16):
+        for dtype in ((torch.bfloat16, torch.float16) if world <= 4 else (torch.bfloat16,)):
             for algo in ("mc_store", "mc_reduce", "p2p"):
                 H, TMAX = 4096, 300
                 try:
@@ -149,7 +149,7 @@ def _worker(rank, world, port, q):
         os._exit(0)
 
 
-@pytest.mark.timeout(200)
+@pytest.mark.timeout(500)
 @pytest.mark.parametrize("world", [2, 4, 8])
 def test_tp_fused_exchange_matches_nccl_plus_norm(world):
     if torch.cuda.device_count() < world:
@@ -161,7 +161,7 @@ def test_tp_fused_exchange_matches_nccl_plus_norm(world):
     for p in procs:
         p.start()
     try:
-        res = [q.get(timeout=150) for _ in range(world)]
+        res = [q.get(timeout=170 if world <= 4 else 400) for _ in range(world)]
     finally:                      # never leave a rank spinning on a GPU behind a failed or timed-out run
         for p in procs:
             p.join(timeout=20)
