@@ -18,6 +18,15 @@ case "$s" in
   vsref)  t 500 python tests/bench_vs_ref_cuda.py --ms 256 64 32 16 1 > gpurun_out/r02_vs_ref.jsonl 2> gpurun_out/r02_vs_ref.err; cut -c1-220 gpurun_out/r02_vs_ref.jsonl ;;
   bench)  t 400 python bench.py > gpurun_out/r02_bench_n1.json 2> gpurun_out/r02_bench_n1.err; tail -c 2500 gpurun_out/r02_bench_n1.json; tail -3 gpurun_out/r02_bench_n1.err ;;
   gptq)   t 400 python bench.py --quant gptq --no-cpu-baseline > gpurun_out/r02_bench_n1_gptq.json 2> gpurun_out/r02_bench_n1_gptq.err; tail -c 1500 gpurun_out/r02_bench_n1_gptq.json; tail -3 gpurun_out/r02_bench_n1_gptq.err ;;
+  ncu)    # evidence captures (one GPU): launch list of a step, full sets of the fp8 attention, both Marlin kernels
+          t 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/r02_launches_step_ncu.csv \
+             python bench.py --steps 1 --warmup 1 --no-secondary --no-ref-cuda --no-cpu-baseline --no-graph > gpurun_out/r02_ncu_step.log 2>&1; tail -1 gpurun_out/r02_ncu_step.log | cut -c1-200
+          t 240 ncu --set full --clock-control none --import-source on -k regex:paged_attention_tc -s 3 -c 1 -o gpurun_out/r02_attn_fp8_cfg4 -f \
+             python tools/bench_attn.py --kv-dtype fp8 --bs 1024 --ctx 8192 --heads 4 --kv-heads 1 --layers 1 --iters 3 > gpurun_out/r02_ncu_attn.log 2>&1; tail -1 gpurun_out/r02_ncu_attn.log | cut -c1-200
+          t 240 ncu --set full --clock-control none --import-source on -k regex:marlin_w4a16_tc5 -s 3 -c 1 -o gpurun_out/r02_marlin_tc5_m256 -f \
+             python tools/bench_marlin.py --m 256 --iters 2 --kn 4096 28672 > gpurun_out/r02_ncu_marlin.log 2>&1; tail -1 gpurun_out/r02_ncu_marlin.log | cut -c1-200
+          t 240 ncu --set full --clock-control none --import-source on -k regex:marlin_w4a16_small -s 3 -c 1 -o gpurun_out/r02_marlin_small_m16 -f \
+             python tools/bench_marlin.py --m 16 --iters 2 --kn 4096 28672 > gpurun_out/r02_ncu_marlin_small.log 2>&1; tail -1 gpurun_out/r02_ncu_marlin_small.log | cut -c1-200 ;;
   full)   t 900 python -m pytest tests -m gpu -q --tb=short -x 2>&1 | tail -12 | tee gpurun_out/r02_pytest_gpu.log ;;
 esac
 done
