@@ -63,6 +63,12 @@ _TABLE = (
     ("convert_fp8", "_C_cache_ops", "output, input, scale=1.0, kv_dtype='fp8'"),
     ("get_device_attribute", "_C_cuda_utils", "attribute, device"),
     ("get_max_shared_memory_per_block_device_attribute", "_C_cuda_utils", "device"),
+    # sampler: probability-space kernels (reference _custom_ops.py: sampling_from_probs ... top_k_mask_logits)
+    ("sampling_from_probs", "_C", "probs, uniform_samples, deterministic=True"),
+    ("top_k_renorm_prob", "_C", "probs, maybe_top_k_arr, top_k_val"),
+    ("top_p_renorm_prob", "_C", "probs, maybe_top_p_arr, top_p_val"),
+    ("top_k_mask_logits", "_C", "logits, maybe_top_k_arr, top_k_val"),
+    ("cutlass_scaled_mm_supports_fp8", "_C", "cuda_device_capability"),
     # NVLink peer-memory all-reduce (opaque handle `fa`)
     ("init_custom_ar", "_C_custom_ar", "meta, rank_data, handles, offsets, rank, full_nvlink"),
     ("all_reduce_reg", "_C_custom_ar", "fa, inp, out"),
@@ -90,5 +96,60 @@ def _emit(name: str, namespace: str, params: str):
 
 for _name, _ns, _params in _TABLE:
     globals()[_name] = _emit(_name, _ns, _params)
-__all__ = [t[0] for t in _TABLE]
 del _name, _ns, _params
+
+
+# ---- wrappers that are more than a forward in the reference too (they allocate outputs / unpack pairs) ---------------
+def top_k_sampling_from_probs(probs, uniform_samples, maybe_top_k_arr, top_k_val, deterministic=True):
+    """(samples int32 [B], success bool [B]); uniform_samples [max_rounds, B] (reference _custom_ops.py + sampling.cu:125)."""
+    return tuple(torch.ops._C.top_k_sampling_from_probs(probs, uniform_samples, maybe_top_k_arr, top_k_val, deterministic))
+
+
+def top_p_sampling_from_probs(probs, uniform_samples, maybe_top_p_arr, top_p_val, deterministic=True):
+    return tuple(torch.ops._C.top_p_sampling_from_probs(probs, uniform_samples, maybe_top_p_arr, top_p_val, deterministic))
+
+
+def min_p_sampling_from_probs(probs, uniform_samples, maybe_min_p_arr, min_p_val, deterministic=True):
+    return tuple(torch.ops._C.min_p_sampling_from_probs(probs, uniform_samples, maybe_min_p_arr, min_p_val, deterministic))
+
+
+def top_k_top_p_sampling_from_probs(probs, uniform_samples, maybe_top_k_arr, top_k_val, maybe_top_p_arr, top_p_val,
+                                    deterministic=True):
+    return tuple(torch.ops._C.top_k_top_p_sampling_from_probs(probs, uniform_samples, maybe_top_k_arr, float(top_k_val),
+                                                              maybe_top_p_arr, top_p_val, deterministic))
+
+
+def scaled_fp8_quant(input, scale=None, num_token_padding=None, scale_ub=None, use_per_token_if_dynamic=False):
+    """Quantise [tokens, hidden] to float8_e4m3fn; returns (output, scale). Static when `scale` is given, else dynamic
+    per tensor or per token — the reference's function of the same name (aphrodite/_custom_ops.py:632-685)."""
+    assert input.ndim == 2
+    shape = input.shape
+    if num_token_padding:
+        shape = (max(num_token_padding, input.shape[0]), shape[1])
+    output = torch.empty(shape, device=input.device, dtype=torch.float8_e4m3fn)
+    if scale is None:
+        if use_per_token_if_dynamic:
+            scale = torch.empty((shape[0], 1), device=input.device, dtype=torch.float32)
+            torch.ops._C.dynamic_per_token_scaled_fp8_quant(output, input, scale, scale_ub)
+        else:
+            scale = torch.zeros(1, device=input.device, dtype=torch.float32)
+            torch.ops._C.dynamic_scaled_fp8_quant(output, input, scale)
+    else:
+        assert scale.numel() == 1 or num_token_padding is None
+        torch.ops._C.static_scaled_fp8_quant(output, input, scale)
+    return output, scale
+
+
+def cutlass_scaled_mm(a, b, scale_a, scale_b, out_dtype, bias=None):
+    """out[M, N] = out_dtype(scale_a * (scale_b * (a @ b)) + bias); a [M, K] row-major, b [K, N] column-major, fp8-e4m3
+    or int8 (reference aphrodite/_custom_ops.py:496-513)."""
+    assert b.shape[0] % 16 == 0 and b.shape[1] % 16 == 0
+    assert out_dtype is torch.bfloat16 or out_dtype is torch.float16
+    assert bias is None or (bias.shape[0] == b.shape[1] and bias.dtype == out_dtype)
+    out = torch.empty((a.shape[0], b.shape[1]), dtype=out_dtype, device=a.device)
+    torch.ops._C.cutlass_scaled_mm(out, a, b, scale_a, scale_b, bias)
+    return out
+
+
+__all__ = [t[0] for t in _TABLE] + ["top_k_sampling_from_probs", "top_p_sampling_from_probs", "min_p_sampling_from_probs",
+                                   "top_k_top_p_sampling_from_probs", "scaled_fp8_quant", "cutlass_scaled_mm"]

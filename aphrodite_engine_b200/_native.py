@@ -74,6 +74,21 @@ SIGNATURES = {
                                c_float] + [c_int] * 6 + [c_void_p],
     "b200_get_device_attribute": [c_int64, c_int64],
     "b200_get_max_shared_memory_per_block_device_attribute": [c_int64],
+    # fp8 activation quantisation, W8A8 GEMM, sampling, prefill attention over the paged cache
+    "b200_static_scaled_fp8_quant": [c_void_p] * 3 + [c_int64, c_int, c_void_p],
+    "b200_dynamic_scaled_fp8_quant": [c_void_p] * 3 + [c_int64, c_int, c_void_p],
+    "b200_dynamic_per_token_scaled_fp8_quant": [c_void_p] * 4 + [c_int] * 3 + [c_void_p],
+    "b200_cutlass_scaled_mm_supports_fp8": [c_int],
+    "b200_scaled_mm_plan": [c_int] * 3,
+    "b200_cutlass_scaled_mm": [c_void_p] * 6 + [c_int] * 3 + [c_int64] * 3 + [c_int] * 5 + [c_void_p],
+    "b200_sampling_from_probs": [c_void_p] * 3 + [c_int] * 3 + [c_void_p],
+    "b200_rejection_sampling_from_probs": [c_int] + [c_void_p] * 5 + [c_int, c_void_p, c_float] + [c_int] * 4 +
+                                          [c_void_p],
+    "b200_top_p_renorm_prob": [c_void_p] * 3 + [c_float] + [c_int] * 2 + [c_void_p],
+    "b200_top_k_renorm_prob": [c_void_p] * 3 + [c_int] * 3 + [c_void_p],
+    "b200_top_k_mask_logits": [c_void_p] * 3 + [c_int] * 3 + [c_void_p],
+    "b200_context_attention_fwd": [c_void_p] * 11 + [c_int] * 7 + [c_int64] * 13 + [c_float] * 3 + [c_int] * 3 +
+                                  [c_void_p],
 }
 _RESTYPES = {
     "b200_tp_flag_bytes": c_int64,

@@ -23,7 +23,8 @@ CORE = os.path.join(PKG, "_core_C.abi3.so")
 MOE = os.path.join(PKG, "_moe_C.abi3.so")
 
 CU_SOURCES = ["runtime.cu", "paged_attention.cu", "cache_ops.cu", "norm_rope_act.cu", "marlin_repack.cu",
-              "marlin_gemm.cu", "marlin_gemm_small.cu", "moe_ops.cu", "custom_all_reduce.cu", "misc_ops.cu", "tp_fused.cu"]
+              "marlin_gemm.cu", "marlin_gemm_small.cu", "moe_ops.cu", "custom_all_reduce.cu", "misc_ops.cu", "tp_fused.cu",
+              "fp8_quant.cu", "scaled_mm.cu", "sampling.cu", "prefill_attention.cu"]
 HEADERS = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + [
     os.path.join(ROOT, "include", "b200_decode.h")]
 
@@ -75,9 +76,9 @@ def build_lib(verbose=False):
 def build_shim(verbose=False, name="_C"):
     import torch
 
-    src = os.path.join(CSRC, "torch_shim.cpp" if name == "_C" else "moe_shim.cpp")
+    srcs = [os.path.join(CSRC, f) for f in (("torch_shim.cpp", "torch_shim_r2.cpp") if name == "_C" else ("moe_shim.cpp",))]
     SHIM = os.path.join(PKG, f"{name}.abi3.so")
-    if not _stale(SHIM, [src, LIB] + HEADERS):
+    if not _stale(SHIM, srcs + [LIB] + HEADERS):
         return SHIM
     tdir = os.path.dirname(torch.__file__)
     abi = int(torch._C._GLIBCXX_USE_CXX11_ABI)
@@ -85,7 +86,7 @@ def build_shim(verbose=False, name="_C"):
     cmd = [
         "g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-w", f"-D_GLIBCXX_USE_CXX11_ABI={abi}",
         "-DTORCH_EXTENSION_NAME=_C", f"-I{tdir}/include", f"-I{tdir}/include/torch/csrc/api/include",
-        f"-I{pyinc}", "-I/usr/local/cuda/include", f"-I{ROOT}/include", src, "-o", SHIM,
+        f"-I{pyinc}", "-I/usr/local/cuda/include", f"-I{ROOT}/include", *srcs, "-o", SHIM,
         f"-L{PKG}", "-lb200decode", f"-L{tdir}/lib", "-ltorch", "-ltorch_cpu", "-ltorch_cuda",
         "-lc10", "-lc10_cuda", "-ltorch_python", "-L/usr/local/cuda/lib64", "-lcudart",
         "-Wl,-rpath,$ORIGIN", f"-Wl,-rpath,{tdir}/lib",

@@ -1,0 +1,371 @@
+// scaled_mm.cu — W8A8 GEMM with per-tensor / per-token / per-channel scales on 5th-gen tensor cores, sm_100a.
+//
+// Replaces cutlass_scaled_mm (kernels/quantization/cutlass_w8a8/scaled_mm_entry.cu:92-140; the CUTLASS 2.x / 3.x
+// kernels behind it, scaled_mm_c2x.cu / scaled_mm_c3x.cu, stop at sm_90 `wgmma` and do not exist for sm_100):
+//     out[M,N] = T( a_scales[m|0] * ( b_scales[n|0] * sum_k a[m,k] * b[k,n] ) + bias[n] )
+//   a  [M,K] row-major, fp8-e4m3 or int8        b [K,N] COLUMN-major (= the checkpoint's [N,K] weight, K contiguous)
+//   a_scales fp32 [1] or [M], b_scales fp32 [1] or [N], bias T [N] or none, out fp16 / bf16
+// Epilogue arithmetic in fp32 in the reference's order (ScaledEpilogue, scaled_mm_c3x.cu: Compute0 = b_scales * acc,
+// Compute1 = a_scales * Compute0, with bias: fma(a_scales, Compute0, bias)); one rounding to T.
+//
+// Design (the transposed formulation of marlin_gemm.cu, without the dequant stage: both operands are already in a
+// tensor-core format and K-major, so they go global -> TMA -> shared memory -> tcgen05 untouched):
+//   D^T[128 channels, tokens <= 256] += W[128 ch, 128 k] . A[tokens, 128 k]^T     one CTA per (128-channel tile,
+//                                                                                  256-token block, k-split)
+//   * both tiles by cp.async.bulk.tensor (SWIZZLE_128B; one 128-byte swizzle row = 128 k of 8-bit data), OOB rows and
+//     the k tail zero-filled by the TMA unit; a 3..8-stage full/empty mbarrier ring
+//   * one elected thread issues 4 x tcgen05.mma.cta_group::1.kind::f8f6f4 (or kind::i8) M=128, N=tokens, K=32 per stage;
+//     fp32 (s32) accumulator in TMEM; tcgen05.commit frees the stage
+//   * epilogue warps tcgen05.ld their TMEM lane quadrant (lane = channel, column = token), apply the scales / bias,
+//     round once and store
+//   * k-split (decode shapes have few tiles: 4096 channels = 32 tiles on 148 SMs): the splits of a tile are the CTAs
+//     of one thread-block cluster (1, 1, S). After the main loop the pipeline buffers are idle, so every split PUSHES
+//     its fp32 partial rows into the shared memory of the split that owns the row (st.shared::cluster, rows
+//     interleaved over the splits), a cluster barrier publishes them, and each split sums ITS rows over the S slots in
+//     split order: deterministic, no global scratch (the op has no workspace argument), no atomics, and the output
+//     rows leave as 256-byte coalesced stores.
+#include "common.cuh"
+#include "tc5.cuh"
+
+#include <algorithm>
+
+namespace b200 {
+
+static constexpr int SM_NT = 128;            // output channels per CTA (UMMA M)
+static constexpr int SM_KC = 128;            // k per stage: one 128-byte swizzle row of 8-bit elements
+static constexpr int SM_TOK = 256;           // tokens per CTA (UMMA N)
+static constexpr int SM_MAX_STAGES = 8;
+static constexpr int SM_W_BYTES = SM_NT * SM_KC;          // 16 KB
+static constexpr int SM_THREADS = 192;       // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+static constexpr int SM_SMEM_TOTAL = 224 * 1024;
+static constexpr int SM_FIXED = 2048;        // barriers + alignment slack
+
+enum { SMK_FP8 = 0, SMK_INT8 = 1 };
+
+struct ScaledMMParams {
+  void* c;                  // [M, N] T, row stride ldc
+  const float* a_scales;    // [1] or [M]
+  const float* b_scales;    // [1] or [N]
+  const void* bias;         // [N] T or nullptr
+  int M, N, K;
+  int64_t ldc;
+  int a_scale_per_token, b_scale_per_channel;
+  int box_rows;             // rows of the activation TMA box (tokens rounded up to 16)
+  int act_bytes;            // box_rows * 128
+  int stages;
+  int split_k, chunks_per_split;
+};
+
+__device__ __forceinline__ uint32_t sm_cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void sm_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void st_remote_u32(uint32_t local_saddr, uint32_t cta_rank, uint32_t v) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_saddr), "r"(cta_rank));
+  asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(remote), "r"(v) : "memory");
+}
+
+template <typename T, int KIND>
+__global__ void __launch_bounds__(SM_THREADS, 1)
+scaled_mm_tc5_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_a,
+                     const ScaledMMParams p) {
+  extern __shared__ uint8_t sm_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sm_smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int NS = p.stages;
+  const int stage_bytes = SM_W_BYTES + p.act_bytes;
+  uint8_t* tiles = smem;                                     // [NS][ W tile 16 KB | activation tile act_bytes ]
+  uint64_t* full = reinterpret_cast<uint64_t*>(tiles + (size_t)NS * stage_bytes);
+  uint64_t* empty = full + SM_MAX_STAGES;
+  uint64_t* accum_full = empty + SM_MAX_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_base = blockIdx.x * SM_NT;
+  const int tok_base = blockIdx.y * SM_TOK;
+  const int toks = min(SM_TOK, p.M - tok_base);
+  const int n_mma = max(16, (toks + 15) & ~15);
+  const int total_chunks = (p.K + SM_KC - 1) / SM_KC;
+  const int chunk0 = blockIdx.z * p.chunks_per_split;
+  const int nchunks = min(p.chunks_per_split, total_chunks - chunk0);     // >= 1 by construction of the split plan
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < n_mma) tmem_cols <<= 1;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < SM_MAX_STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(accum_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      int s = 0;
+      uint32_t use = 0;
+      const uint32_t tx_bytes = (uint32_t)SM_W_BYTES + (uint32_t)p.box_rows * 128u;   // TMA always moves the full boxes
+      for (int c = 0; c < nchunks; ++c) {
+        if (use > 0) mbar_wait(&empty[s], (use - 1) & 1u);
+        uint8_t* st = tiles + (size_t)s * stage_bytes;
+        mbar_arrive_expect_tx(&full[s], tx_bytes);
+        tma_load_2d(st, &tmap_w, &full[s], (chunk0 + c) * SM_KC, n_base);
+        tma_load_2d(st + SM_W_BYTES, &tmap_a, &full[s], (chunk0 + c) * SM_KC, tok_base);
+        if (++s == NS) { s = 0; ++use; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (elect_one()) {
+      // instruction descriptor (cute::UMMA::InstrDescriptor): c_format [4,6) 1 = F32 / 2 = S32; a/b format [7,10),[10,13)
+      // 0 = E4M3 (kind::f8f6f4) / 1 = signed 8-bit (kind::i8); both operands K-major; N >> 3 at [17,23); M >> 4 at [24,29)
+      const uint32_t idesc = KIND == SMK_FP8
+                                 ? ((1u << 4) | ((uint32_t)(n_mma >> 3) << 17) | ((uint32_t)(SM_NT >> 4) << 24))
+                                 : ((2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n_mma >> 3) << 17) |
+                                    ((uint32_t)(SM_NT >> 4) << 24));
+      int s = 0;
+      uint32_t use = 0;
+      for (int c = 0; c < nchunks; ++c) {
+        mbar_wait(&full[s], use & 1u);
+        tc_fence_after();
+        const uint32_t st = smem_u32(tiles + (size_t)s * stage_bytes);
+        const uint64_t a_desc = make_sw128_desc(st);                   // weights: UMMA "A" (M = channels)
+        const uint64_t b_desc = make_sw128_desc(st + SM_W_BYTES);      // activations: UMMA "B" (N = tokens)
+#pragma unroll
+        for (int ks = 0; ks < SM_KC / 32; ++ks) {
+          // 32 k = 32 bytes further inside the 128-byte swizzle row = +2 in the descriptor's (address >> 4) field
+          if constexpr (KIND == SMK_FP8)
+            umma_f8(tmem_d, a_desc + (uint64_t)(2 * ks), b_desc + (uint64_t)(2 * ks), idesc, (c > 0 || ks > 0) ? 1u : 0u);
+          else
+            umma_i8(tmem_d, a_desc + (uint64_t)(2 * ks), b_desc + (uint64_t)(2 * ks), idesc, (c > 0 || ks > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty[s]);          // frees stage s when these MMAs retire
+        if (++s == NS) { s = 0; ++use; }
+      }
+      umma_commit(accum_full);
+    }
+  }
+
+  const int S = p.split_k;
+  const uint32_t rank = S > 1 ? sm_cluster_rank() : 0u;
+  const int rows_per = (toks + S - 1) / S;                      // token rows of this tile owned by one split
+  uint32_t* red = reinterpret_cast<uint32_t*>(tiles);           // [S slots][rows_per][128 ch] 32-bit partials (S > 1)
+
+  if (S > 1) {
+    // every split of the tile has finished reading its pipeline buffers before anyone pushes partials into them
+    if (warp >= 2) { mbar_wait(accum_full, 0); tc_fence_after(); }
+    __syncthreads();
+    sm_cluster_sync();
+  }
+
+  if (warp >= 2) {
+    // ===================== epilogue =====================
+    if (S == 1) { mbar_wait(accum_full, 0); tc_fence_after(); }
+    const int quad = warp & 3;                                   // TMEM lanes 32*quad .. +31 belong to this warp
+    const int chl = quad * 32 + lane;
+    const int ch = n_base + chl;
+    const bool ch_ok = ch < p.N;
+    T* cptr = reinterpret_cast<T*>(p.c);
+    float bs = 0.f, bv = 0.f;
+    if (ch_ok) {
+      bs = p.b_scale_per_channel ? __ldg(p.b_scales + ch) : __ldg(p.b_scales);
+      if (p.bias != nullptr) bv = to_f32<T>(reinterpret_cast<const T*>(p.bias)[ch]);
+    }
+    const bool has_bias = p.bias != nullptr;
+    for (int col0 = 0; col0 < n_mma; col0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)col0, v);
+      if (S == 1) {
+        float as_l = 1.f;
+        if (col0 + lane < toks) as_l = p.a_scale_per_token ? __ldg(p.a_scales + tok_base + col0 + lane) : __ldg(p.a_scales);
+#pragma unroll
+        for (int t = 0; t < 32; ++t) {
+          const float as = __shfl_sync(0xffffffffu, as_l, t);
+          if (ch_ok && col0 + t < toks) {
+            const float acc = KIND == SMK_FP8 ? __uint_as_float(v[t]) : (float)(int)v[t];
+            const float tmp = bs * acc;
+            const float o = has_bias ? fmaf(as, tmp, bv) : as * tmp;
+            cptr[(size_t)(tok_base + col0 + t) * p.ldc + ch] = from_f32<T>(o);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int t = 0; t < 32; ++t) {
+          const int tok = col0 + t;
+          if (tok < toks) {
+            const uint32_t owner = (uint32_t)(tok % S);
+            const uint32_t row = (uint32_t)(tok / S);
+            st_remote_u32(smem_u32(red + ((size_t)rank * rows_per + row) * SM_NT + chl), owner, v[t]);
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+
+  if (S > 1) {
+    __syncthreads();
+    sm_cluster_sync();                 // all partial rows have landed in their owners' shared memory
+    if (warp >= 2) {
+      const int chl = threadIdx.x - 64;                         // 128 epilogue threads = 128 channels: coalesced rows
+      const int ch = n_base + chl;
+      if (ch < p.N) {
+        T* cptr = reinterpret_cast<T*>(p.c);
+        const float bs = p.b_scale_per_channel ? __ldg(p.b_scales + ch) : __ldg(p.b_scales);
+        const bool has_bias = p.bias != nullptr;
+        const float bv = has_bias ? to_f32<T>(reinterpret_cast<const T*>(p.bias)[ch]) : 0.f;
+        for (int row = 0; (int)rank + row * S < toks; ++row) {
+          const int tok = (int)rank + row * S;
+          float acc;
+          if constexpr (KIND == SMK_FP8) {
+            acc = 0.f;
+            for (int z = 0; z < S; ++z) acc += __uint_as_float(red[((size_t)z * rows_per + row) * SM_NT + chl]);   // split order
+          } else {
+            int iacc = 0;
+            for (int z = 0; z < S; ++z) iacc += (int)red[((size_t)z * rows_per + row) * SM_NT + chl];
+            acc = (float)iacc;
+          }
+          const float as = p.a_scale_per_token ? __ldg(p.a_scales + tok_base + tok) : __ldg(p.a_scales);
+          const float tmp = bs * acc;
+          const float o = has_bias ? fmaf(as, tmp, bv) : as * tmp;
+          cptr[(size_t)(tok_base + tok) * p.ldc + ch] = from_f32<T>(o);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_d, tmem_cols);
+  }
+}
+
+// 2-D tensor map over a K-contiguous 8-bit matrix [rows, K] with row stride `ld` bytes; box [128 k x box_rows]
+static int encode_u8_map(CUtensorMap* tmap, const void* base, int64_t rows, int K, int64_t ld, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  B200_CHECK(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+  const cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)ld};
+  const cuuint32_t box[2] = {(cuuint32_t)SM_KC, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  B200_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed: " + std::to_string((int)r));
+  return 0;
+}
+
+// k-splits of one tile: enough to fill one wave of the SMs, at least 4 chunks (512 k) each, at most 8 (portable cluster)
+static int plan_scaled_mm_split(int M, int N, int K) {
+  const int tiles = ((N + SM_NT - 1) / SM_NT) * ((M + SM_TOK - 1) / SM_TOK);
+  const int chunks = (K + SM_KC - 1) / SM_KC;
+  int split = std::min(std::min(num_sms() / std::max(tiles, 1), chunks / 4), 8);
+  if (split < 1) split = 1;
+  while (split > 1 && (split - 1) * ((chunks + split - 1) / split) >= chunks) --split;     // never an empty split
+  return split;
+}
+
+template <typename T, int KIND>
+static int launch_scaled_mm(const CUtensorMap& tw, const CUtensorMap& ta, ScaledMMParams& p, dim3 grid, cudaStream_t st) {
+  auto kern = scaled_mm_tc5_kernel<T, KIND>;
+  static thread_local uint64_t attr_done = 0;
+  int dev = 0;
+  B200_CUDA_OK(cudaGetDevice(&dev));
+  if (!(attr_done >> (dev & 63) & 1)) {
+    B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_SMEM_TOTAL));
+    attr_done |= 1ull << (dev & 63);
+  }
+  const int stage_bytes = SM_W_BYTES + p.act_bytes;
+  p.stages = std::min(SM_MAX_STAGES, (SM_SMEM_TOTAL - SM_FIXED) / stage_bytes);
+  B200_CHECK(p.stages >= 2, "scaled_mm: shared-memory plan leaves fewer than two pipeline stages");
+  const size_t smem = (size_t)p.stages * stage_bytes + SM_FIXED;
+  // the k-split reduction reuses the pipeline buffers: [S][ceil(tokens / S)][128] 32-bit partials
+  if (p.split_k > 1) {
+    const int toks = std::min(p.M, SM_TOK);
+    const size_t need = (size_t)p.split_k * ((toks + p.split_k - 1) / p.split_k) * SM_NT * 4;
+    B200_CHECK(need <= (size_t)p.stages * stage_bytes, "scaled_mm: k-split reduction buffer does not fit");
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(SM_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = (unsigned)p.split_k;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  B200_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tw, ta, p));
+  return check_launch("scaled_mm_tc5_kernel");
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_scaled_mm_plan(int size_m, int size_n, int size_k) {
+  if (size_m <= 0 || size_n <= 0 || size_k <= 0) return 1;
+  return plan_scaled_mm_split(size_m, size_n, size_k);
+}
+
+extern "C" int b200_cutlass_scaled_mm_supports_fp8(int cuda_device_capability) {
+  // the reference answers for its CUTLASS kernels (scaled_mm_entry.cu:66-80: sm_89 with CUDA >= 12.4, sm_90+); this
+  // library is the sm_100a implementation
+  return cuda_device_capability >= 100 ? 1 : 0;
+}
+
+extern "C" int b200_cutlass_scaled_mm(void* out, const void* a, const void* b, const float* a_scales,
+                                      const float* b_scales, const void* bias, int size_m, int size_n, int size_k,
+                                      int64_t lda, int64_t ldb, int64_t ldc, int a_scales_numel, int b_scales_numel,
+                                      int ab_dtype, int out_dtype, int split_k, void* stream) {
+  B200_CHECK(ab_dtype == B200_AB_FP8_E4M3 || ab_dtype == B200_AB_INT8, "cutlass_scaled_mm: a and b must be float8_e4m3fn or int8");
+  B200_CHECK(out_dtype == B200_F16 || out_dtype == B200_BF16, "cutlass_scaled_mm: out must be float16 or bfloat16");
+  B200_CHECK(size_m >= 0 && size_n > 0 && size_k > 0, "cutlass_scaled_mm: invalid problem size");
+  B200_CHECK(a_scales_numel == 1 || a_scales_numel == size_m, "a_scales must hold 1 or M values");
+  B200_CHECK(b_scales_numel == 1 || b_scales_numel == size_n, "b_scales must hold 1 or N values");
+  B200_CHECK(size_k % 16 == 0 && lda % 16 == 0 && ldb % 16 == 0, "K, a.stride(0) and b.stride(1) must be multiples of 16 (16-byte alignment)");
+  B200_CHECK((reinterpret_cast<uintptr_t>(a) & 15) == 0 && (reinterpret_cast<uintptr_t>(b) & 15) == 0,
+             "a and b must be 16-byte aligned");
+  B200_CHECK(lda >= size_k && ldb >= size_k && ldc >= size_n, "leading dimensions smaller than the row length");
+  if (size_m == 0) return 0;
+  const int toks = std::min(size_m, SM_TOK);
+  const int box_rows = std::max(16, (toks + 15) & ~15);
+  CUtensorMap tw, ta;
+  if (int rc = encode_u8_map(&tw, b, size_n, size_k, ldb, SM_NT)) return rc;
+  if (int rc = encode_u8_map(&ta, a, size_m, size_k, lda, box_rows)) return rc;
+  ScaledMMParams p{};
+  p.c = out; p.a_scales = a_scales; p.b_scales = b_scales; p.bias = bias;
+  p.M = size_m; p.N = size_n; p.K = size_k; p.ldc = ldc;
+  p.a_scale_per_token = (a_scales_numel > 1 || size_m == 1) ? 1 : 0;
+  p.b_scale_per_channel = (b_scales_numel > 1 || size_n == 1) ? 1 : 0;
+  if (a_scales_numel == 1) p.a_scale_per_token = 0;
+  if (b_scales_numel == 1) p.b_scale_per_channel = 0;
+  p.box_rows = box_rows;
+  p.act_bytes = box_rows * 128;
+  const int chunks = (size_k + SM_KC - 1) / SM_KC;
+  if (split_k <= 0) split_k = plan_scaled_mm_split(size_m, size_n, size_k);
+  split_k = std::max(1, std::min(std::min(split_k, 8), chunks));
+  while (split_k > 1 && (split_k - 1) * ((chunks + split_k - 1) / split_k) >= chunks) --split_k;
+  p.split_k = split_k;
+  p.chunks_per_split = (chunks + split_k - 1) / split_k;
+  dim3 grid((size_n + SM_NT - 1) / SM_NT, (size_m + SM_TOK - 1) / SM_TOK, split_k);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (ab_dtype == B200_AB_FP8_E4M3) {
+    if (out_dtype == B200_BF16) return launch_scaled_mm<__nv_bfloat16, SMK_FP8>(tw, ta, p, grid, st);
+    return launch_scaled_mm<__half, SMK_FP8>(tw, ta, p, grid, st);
+  }
+  if (out_dtype == B200_BF16) return launch_scaled_mm<__nv_bfloat16, SMK_INT8>(tw, ta, p, grid, st);
+  return launch_scaled_mm<__half, SMK_INT8>(tw, ta, p, grid, st);
+}

@@ -297,6 +297,78 @@ int b200_advance_step_flashattn(int num_seqs, int num_queries, int block_size, i
                                 int64_t* slot_mapping, const int32_t* block_tables, int64_t block_tables_stride,
                                 void* stream);
 
+/* ---- fp8 activation quantisation ---------------------------------------------------------
+ * replaces static_scaled_fp8_quant            kernels/quantization/fp8/common.cu:260-277 (schema torch_bindings.cpp:375)
+ *          dynamic_scaled_fp8_quant           :279-299 (schema :380-382)  — *scale must be <= 0 on entry (the caller zeroes it)
+ *          dynamic_per_token_scaled_fp8_quant :301-321 (schema :386-390)  — scale_ub fp32 [1] or NULL
+ * out is float8_e4m3fn (1 byte / element), input float / half / bfloat16 (dtype code), contiguous. Results are
+ * bit-identical to the reference kernels (multiply by 1/scale per tensor, divide by the scale per token). */
+int b200_static_scaled_fp8_quant(void* out, const void* input, const float* scale, int64_t numel, int dtype,
+                                 void* stream);
+int b200_dynamic_scaled_fp8_quant(void* out, const void* input, float* scale, int64_t numel, int dtype,
+                                  void* stream);
+int b200_dynamic_per_token_scaled_fp8_quant(void* out, const void* input, float* scales, const float* scale_ub,
+                                            int num_tokens, int hidden_size, int dtype, void* stream);
+
+/* ---- W8A8 GEMM with scales ---------------------------------------------------------------
+ * replaces cutlass_scaled_mm               kernels/quantization/cutlass_w8a8/scaled_mm_entry.cu:92-140 (schema
+ *                                          torch_bindings.cpp:235-239, prototype kernels/ops.h)
+ *          cutlass_scaled_mm_supports_fp8  scaled_mm_entry.cu:66-80 (schema torch_bindings.cpp:243-244)
+ * out[M,N] = T(a_scales[m|0] * (b_scales[n|0] * sum_k a[m,k] b[k,n]) + bias[n]); a [M,K] row-major (row stride lda),
+ * b [K,N] COLUMN-major (column stride ldb, i.e. the [N,K] weight), both float8_e4m3fn or both int8 (ab_dtype);
+ * out fp16 / bf16 (out_dtype), row stride ldc; a_scales / b_scales fp32 with 1 or M / N entries; bias T [N] or NULL.
+ * split_k <= 0 lets the library choose (b200_scaled_mm_plan). tcgen05 kind::f8f6f4 / kind::i8, no workspace. Not
+ * implemented (clear error from the torch op): the asymmetric variant cutlass_scaled_mm_azp. */
+enum { B200_AB_FP8_E4M3 = 0, B200_AB_INT8 = 1 };
+int b200_cutlass_scaled_mm_supports_fp8(int cuda_device_capability);
+int b200_scaled_mm_plan(int size_m, int size_n, int size_k);
+int b200_cutlass_scaled_mm(void* out, const void* a, const void* b, const float* a_scales, const float* b_scales,
+                           const void* bias, int size_m, int size_n, int size_k, int64_t lda, int64_t ldb,
+                           int64_t ldc, int a_scales_numel, int b_scales_numel, int ab_dtype, int out_dtype,
+                           int split_k, void* stream);
+
+/* ---- sampling --------------------------------------------------------------------------------
+ * replaces sampling_from_probs, top_k_ / top_p_ / min_p_ / top_k_top_p_sampling_from_probs, top_p_renorm_prob,
+ *          top_k_renorm_prob, top_k_mask_logits      kernels/sampling/sampling.cu:43-390 (schemas
+ *          torch_bindings.cpp:294-350, prototypes kernels/ops.h:116-145)
+ * probs / logits fp32 [batch, vocab] contiguous; uniform_samples fp32 [batch] (sampling_from_probs) or
+ * [max_rounds, batch]; samples int32 [batch]; success bool [batch] (1 byte each) or NULL; per-row parameter arrays may
+ * be NULL (then the scalar applies). Same uniforms -> same token as the reference's rejection loop; `deterministic` is
+ * accepted for the signature and ignored (every kernel here is deterministic). */
+enum { B200_SAMPLE_TOP_K = 0, B200_SAMPLE_TOP_P = 1, B200_SAMPLE_MIN_P = 2, B200_SAMPLE_TOP_K_TOP_P = 3 };
+int b200_sampling_from_probs(const float* probs, const float* uniform_samples, int32_t* samples, int batch_size,
+                             int vocab_size, int deterministic, void* stream);
+/* mode TOP_K: (top_k_arr | top_k_val); TOP_P and MIN_P: (top_p_arr | top_p_val) carry p resp. min_p; TOP_K_TOP_P: both */
+int b200_rejection_sampling_from_probs(int mode, const float* probs, const float* uniform_samples, int32_t* samples,
+                                       uint8_t* success, const int32_t* top_k_arr, int top_k_val,
+                                       const float* top_p_arr, float top_p_val, int batch_size, int vocab_size,
+                                       int max_rounds, int deterministic, void* stream);
+int b200_top_p_renorm_prob(const float* probs, float* renorm_probs, const float* top_p_arr, float top_p_val,
+                           int batch_size, int vocab_size, void* stream);
+int b200_top_k_renorm_prob(const float* probs, float* renorm_probs, const int32_t* top_k_arr, int top_k_val,
+                           int batch_size, int vocab_size, void* stream);
+int b200_top_k_mask_logits(const float* logits, float* masked_logits, const int32_t* top_k_arr, int top_k_val,
+                           int batch_size, int vocab_size, void* stream);
+
+/* ---- prefix-aware prefill attention over the paged cache -------------------------------------
+ * replaces context_attention_fwd   aphrodite/attention/ops/prefix_prefill.py:696-858 (Triton; reached through
+ *                                  PagedAttention.forward_prefix, attention/ops/paged_attn.py:192-228)
+ * q / out [num_tokens, num_heads, D], k / v [num_tokens, num_kv_heads, D] (strides in elements: *_stride_t per token,
+ * *_stride_h per head, innermost contiguous); key_cache [NB, Hkv, D/x, BS, x], value_cache [NB, Hkv, D, BS] (the
+ * paged-attention layouts; block / head strides in cache elements); block_tables int32 [batch, *] (row stride
+ * bt_stride); start_loc int32 [batch] first query token of each sequence; seq_lens int32 [batch] = context + query
+ * length; ctx_lens int32 [batch]; alibi_slopes fp32 [num_heads] or NULL; sliding_window <= 0 disables it.
+ * The reference fixes scale = 1 / sqrt(D) internally (:742); it is a parameter here and the glue passes that value.
+ * Head sizes 64 / 80 / 96 / 112 / 128 / 192 / 256, block sizes 8 / 16 / 32 / 64, fp16 / bf16, kv cache auto / fp8. */
+int b200_context_attention_fwd(
+    const void* q, const void* k, const void* v, void* out, const void* key_cache, const void* value_cache,
+    const int32_t* block_tables, const int32_t* start_loc, const int32_t* seq_lens, const int32_t* ctx_lens,
+    const float* alibi_slopes, int batch, int num_heads, int num_kv_heads, int head_size, int block_size, int x,
+    int max_query_len, int64_t q_stride_t, int64_t q_stride_h, int64_t k_stride_t, int64_t k_stride_h,
+    int64_t v_stride_t, int64_t v_stride_h, int64_t o_stride_t, int64_t o_stride_h, int64_t kc_block_stride,
+    int64_t kc_head_stride, int64_t vc_block_stride, int64_t vc_head_stride, int64_t bt_stride, float scale,
+    float k_scale, float v_scale, int sliding_window, int dtype, int kv_dtype, void* stream);
+
 /* ---- device queries -----------------------------------------------------------------------------
  * replaces get_device_attribute / get_max_shared_memory_per_block_device_attribute
  *          kernels/cuda_utils_kernels.cu (schema torch_bindings.cpp:497-504) */

@@ -13,6 +13,7 @@ translation units with nvcc directly — not the reference's CMake build, which 
     activation_kernels.cu  permute_cols.cu  prepare_inputs/advance_step.cu
     quantization/gptq_marlin/{gptq_marlin,gptq_marlin_repack,awq_marlin_repack}.cu  quantization/awq/gemm_kernels.cu
     moe/{align_block_size_kernel,softmax,marlin_moe_ops}.cu  all_reduce/custom_all_reduce.cu
+    quantization/fp8/common.cu  sampling/sampling.cu
 
 with the flags of cmake/utils.cmake:93-111 (torch's COMMON_NVCC_FLAGS minus the __CUDA_NO_HALF* set, -DENABLE_FP8)
 and `-gencode arch=compute_100a,code=sm_100a`. Registration: oracle/ref_cuda_bindings.cpp (namespace _ref_cuda_C).
@@ -46,6 +47,8 @@ CU_SRCS = [
     "moe/align_block_size_kernel.cu",
     "moe/softmax.cu",
     "moe/marlin_moe_ops.cu",
+    "quantization/fp8/common.cu",        # static / dynamic / per-token scaled_fp8_quant (round 2: §8 f4)
+    "sampling/sampling.cu",              # sampling_from_probs, top-k / top-p / min-p samplers, renorm, mask (§8 f2)
 ]
 # the reference's own TP all-reduce (the N > 1 legs of bench.py's ref_cuda arm): its own library, it needs libcuda
 AR_SRC = "all_reduce/custom_all_reduce.cu"

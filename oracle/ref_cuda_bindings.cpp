@@ -63,4 +63,16 @@ TORCH_LIBRARY(_ref_cuda_C, m) {
   m.def("marlin_gemm_moe", &marlin_gemm_moe);
   m.def("advance_step_flashattn", &advance_step_flashattn);
   m.def("permute_cols", &permute_cols);
+  // round 2: fp8 activation quantisation (kernels/quantization/fp8/common.cu) and the sampling kernels (kernels/sampling/sampling.cu)
+  m.def("static_scaled_fp8_quant", &static_scaled_fp8_quant);
+  m.def("dynamic_scaled_fp8_quant", &dynamic_scaled_fp8_quant);
+  m.def("dynamic_per_token_scaled_fp8_quant", &dynamic_per_token_scaled_fp8_quant);
+  m.def("sampling_from_probs", &sampling_from_probs);
+  m.def("top_p_sampling_from_probs", &top_p_sampling_from_probs);
+  m.def("top_k_sampling_from_probs", &top_k_sampling_from_probs);
+  m.def("min_p_sampling_from_probs", &min_p_sampling_from_probs);
+  m.def("top_k_top_p_sampling_from_probs", &top_k_top_p_sampling_from_probs);
+  m.def("top_p_renorm_prob", &top_p_renorm_prob);
+  m.def("top_k_renorm_prob", &top_k_renorm_prob);
+  m.def("top_k_mask_logits", &top_k_mask_logits);
 }

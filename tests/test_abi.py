@@ -117,6 +117,33 @@ REF_SCHEMAS = {
     "_C_custom_ar::all_reduce_reg": "all_reduce_reg(int fa, Tensor inp, Tensor! out) -> ()",
     "_C_custom_ar::all_reduce_unreg": "all_reduce_unreg(int fa, Tensor inp, Tensor reg_buffer, Tensor! out) -> ()",
     "_C_custom_ar::register_buffer": "register_buffer(int fa, Tensor t, str[] handles, int[] offsets) -> ()",
+    # round 2, SURVEY §8(f): kernels/torch_bindings.cpp:235-253 (W8A8 GEMM), :294-350 (sampling), :374-390 (fp8 quant)
+    "_C::cutlass_scaled_mm":
+        "cutlass_scaled_mm(Tensor! out, Tensor a, Tensor b, Tensor a_scales, Tensor b_scales, Tensor? bias) -> ()",
+    "_C::cutlass_scaled_mm_supports_fp8": "cutlass_scaled_mm_supports_fp8(int cuda_device_capability) -> bool",
+    "_C::cutlass_scaled_mm_azp":
+        "cutlass_scaled_mm_azp(Tensor! out, Tensor a, Tensor b, Tensor a_scales, Tensor b_scales, Tensor azp_adj,"
+        " Tensor? azp, Tensor? bias) -> ()",
+    "_C::sampling_from_probs": "sampling_from_probs(Tensor probs, Tensor uniform_samples, bool deterministic) -> Tensor",
+    "_C::top_k_sampling_from_probs":
+        "top_k_sampling_from_probs(Tensor probs, Tensor uniform_samples, Tensor? maybe_top_k_arr, int top_k_val,"
+        " bool deterministic) -> Tensor[]",
+    "_C::min_p_sampling_from_probs":
+        "min_p_sampling_from_probs(Tensor probs, Tensor uniform_samples, Tensor? maybe_min_p_arr, float min_p_val,"
+        " bool deterministic) -> Tensor[]",
+    "_C::top_p_sampling_from_probs":
+        "top_p_sampling_from_probs(Tensor probs, Tensor uniform_samples, Tensor? maybe_top_p_arr, float top_p_val,"
+        " bool deterministic) -> Tensor[]",
+    "_C::top_k_top_p_sampling_from_probs":
+        "top_k_top_p_sampling_from_probs(Tensor probs, Tensor uniform_samples, Tensor? maybe_top_k_arr,"
+        " float top_k_val, Tensor? maybe_top_p_arr, float top_p_val, bool deterministic) -> Tensor[]",
+    "_C::top_k_renorm_prob": "top_k_renorm_prob(Tensor probs, Tensor? maybe_top_k_arr, int top_k_val) -> Tensor",
+    "_C::top_p_renorm_prob": "top_p_renorm_prob(Tensor probs, Tensor? maybe_top_p_arr, float top_p_val) -> Tensor",
+    "_C::top_k_mask_logits": "top_k_mask_logits(Tensor logits, Tensor? maybe_top_k_arr, int top_k_val) -> Tensor",
+    "_C::static_scaled_fp8_quant": "static_scaled_fp8_quant(Tensor! out, Tensor input, Tensor scale) -> ()",
+    "_C::dynamic_scaled_fp8_quant": "dynamic_scaled_fp8_quant(Tensor! out, Tensor input, Tensor! scale) -> ()",
+    "_C::dynamic_per_token_scaled_fp8_quant":
+        "dynamic_per_token_scaled_fp8_quant(Tensor! out, Tensor input, Tensor! scale, Tensor? scale_ub) -> ()",
     "_C_cuda_utils::get_device_attribute": "get_device_attribute(int attribute, int device_id) -> int",
     "_C_cuda_utils::get_max_shared_memory_per_block_device_attribute":
         "get_max_shared_memory_per_block_device_attribute(int device_id) -> int",
