@@ -151,5 +151,8 @@ def cutlass_scaled_mm(a, b, scale_a, scale_b, out_dtype, bias=None):
     return out
 
 
+# wrappers written out by hand (they allocate / unpack, in the reference as well); everything else comes from _TABLE
+COMPOSITE = ("top_k_sampling_from_probs", "top_p_sampling_from_probs", "min_p_sampling_from_probs",
+             "top_k_top_p_sampling_from_probs", "scaled_fp8_quant", "cutlass_scaled_mm")
 __all__ = [t[0] for t in _TABLE] + ["top_k_sampling_from_probs", "top_p_sampling_from_probs", "min_p_sampling_from_probs",
                                    "top_k_top_p_sampling_from_probs", "scaled_fp8_quant", "cutlass_scaled_mm"]

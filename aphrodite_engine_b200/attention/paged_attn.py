@@ -1,5 +1,5 @@
-"""Decode-side attention glue with the reference's interface (`PagedAttention` in aphrodite/attention/ops/paged_attn.py:
-cache shape :49-56, views :58-72, writer :74-95, decode dispatch :97-190), over this package's ops.
+"""Attention glue with the reference's interface (`PagedAttention` in aphrodite/attention/ops/paged_attn.py:
+cache shape :49-56, views :58-72, writer :74-95, decode dispatch :97-190, prefix prefill :192-228), over this package's ops.
 
 Kept from the reference because callers and checkpointed caches depend on it: the `[2, num_blocks, block*heads*dim]`
 allocation viewed as K `[blocks, kv_heads, dim/x, block, x]` (x = 16 bytes of elements) and V `[blocks, kv_heads, dim,
@@ -76,3 +76,18 @@ class PagedAttention:
         tmp_out = torch.empty(stats_shape + (head_size, ), dtype=out.dtype, device=out.device)
         cls._ops.paged_attention_v2(out, exp_sums, max_logits, tmp_out, query, key_cache, value_cache, *common)
         return out
+
+    @staticmethod
+    def forward_prefix(query: torch.Tensor, key: torch.Tensor, value: torch.Tensor, kv_cache_dtype: str,
+                       key_cache: torch.Tensor, value_cache: torch.Tensor, block_tables: torch.Tensor,
+                       query_start_loc: torch.Tensor, seq_lens_tensor: torch.Tensor, context_lens: torch.Tensor,
+                       max_query_len: int, alibi_slopes: Optional[torch.Tensor], sliding_window: Optional[int],
+                       k_scale: float, v_scale: float) -> torch.Tensor:
+        """Prefill with cached context: query tokens attend to the paged cache and, causally, to this step's keys.
+        query_start_loc has batch + 1 entries (the reference drops the last one the same way, :216-217)."""
+        from .prefix_prefill import context_attention_fwd
+        output = torch.empty_like(query)
+        context_attention_fwd(query, key, value, output, kv_cache_dtype, key_cache, value_cache, block_tables,
+                              query_start_loc[:-1], seq_lens_tensor, context_lens, max_query_len, k_scale, v_scale,
+                              alibi_slopes, sliding_window)
+        return output

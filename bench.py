@@ -759,7 +759,13 @@ def secondary_legs(env, args, model, st, host, shape, num_blocks, dtype, peaks):
         import bench_secondary
     except ImportError:
         return {"note": "bench_secondary.py not present"}
-    return bench_secondary.run(env, args, model, st, host, shape, num_blocks, dtype, peaks)
+    out = bench_secondary.run(env, args, model, st, host, shape, num_blocks, dtype, peaks)
+    try:                                   # prefill attention, sampler kernels, W8A8 (single-GPU legs)
+        import bench_f_rows
+        out.update(bench_f_rows.run(env, peaks))
+    except Exception as e:
+        out["f_rows"] = {"error": repr(e)[:300]}
+    return out
 
 
 def main():

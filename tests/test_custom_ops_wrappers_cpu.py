@@ -45,7 +45,10 @@ def _dummy(arg):
     raise AssertionError(f"unhandled schema type {t}")
 
 
-@pytest.mark.parametrize("name", ops.__all__)
+TABLE_NAMES = [n for n in ops.__all__ if n not in ops.COMPOSITE]
+
+
+@pytest.mark.parametrize("name", TABLE_NAMES)
 def test_wrapper_signature_matches_its_op_schema(name):
     sig = inspect.signature(getattr(ops, name))
     schema = _schema(name)
@@ -79,7 +82,7 @@ def test_reference_defaults_are_kept():
     assert list(inspect.signature(ops.fused_add_rms_norm).parameters) == ["input", "residual", "weight", "epsilon"]
 
 
-@pytest.mark.parametrize("name", [n for n in ops.__all__])
+@pytest.mark.parametrize("name", TABLE_NAMES)
 def test_wrapper_reaches_the_dispatcher_and_has_no_cpu_path(name):
     schema = _schema(name)
     if not any("Tensor" in str(a.type) for a in schema.arguments):
@@ -89,3 +92,29 @@ def test_wrapper_reaches_the_dispatcher_and_has_no_cpu_path(name):
         getattr(ops, name)(*args)
     msg = str(ei.value)
     assert "CPU" in msg or "cuda" in msg.lower() or "GPU" in msg, msg[:300]
+
+
+def test_composite_wrappers_keep_reference_signatures_and_have_no_cpu_path():
+    """The hand-written wrappers (aphrodite/_custom_ops.py:496-513 cutlass_scaled_mm, :632-685 scaled_fp8_quant, the
+    sampling pairs): parameter names / defaults of the reference, and CPU tensors end in the dispatcher's error."""
+    assert list(inspect.signature(ops.scaled_fp8_quant).parameters) == [
+        "input", "scale", "num_token_padding", "scale_ub", "use_per_token_if_dynamic"]
+    assert list(inspect.signature(ops.cutlass_scaled_mm).parameters) == ["a", "b", "scale_a", "scale_b", "out_dtype", "bias"]
+    assert list(inspect.signature(ops.top_k_top_p_sampling_from_probs).parameters) == [
+        "probs", "uniform_samples", "maybe_top_k_arr", "top_k_val", "maybe_top_p_arr", "top_p_val", "deterministic"]
+    x = torch.randn(4, 32)
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        ops.scaled_fp8_quant(x)
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        ops.scaled_fp8_quant(x, use_per_token_if_dynamic=True)
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        ops.scaled_fp8_quant(x, torch.ones(1))
+    a = torch.zeros(4, 32).to(torch.float8_e4m3fn)
+    b = torch.zeros(16, 32).to(torch.float8_e4m3fn).t()
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        ops.cutlass_scaled_mm(a, b, torch.ones(1), torch.ones(1), torch.bfloat16)
+    p = torch.full((2, 8), 0.125)
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        ops.top_k_sampling_from_probs(p, torch.rand(4, 2), None, 2)
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        ops.sampling_from_probs(p, torch.rand(2))
