@@ -114,8 +114,19 @@ __global__ void __launch_bounds__(1024) fp8_quant_token_kernel(uint8_t* __restri
   const T* row = in + (int64_t)blockIdx.x * hidden;
   uint8_t* orow = out + (int64_t)blockIdx.x * hidden;
   const bool vec = vec_ok(row, orow, hidden);
+  // rows of up to 8 elements per thread (hidden <= 8192 at 1024 threads) stay in registers between the absmax pass and
+  // the conversion: the row crosses HBM / L2 once
+  const bool keep = vec && hidden <= (int)blockDim.x * 8;
+  float kept[8];
+  const bool mine = keep && (int)threadIdx.x * 8 < hidden;
   float m = 0.f;
-  if (vec) {
+  if (keep) {
+    if (mine) {
+      load8(row + threadIdx.x * 8, kept);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) m = fmaxf(m, fabsf(kept[j]));
+    }
+  } else if (vec) {
     for (int i = threadIdx.x * 8; i < hidden; i += blockDim.x * 8) {
       float f[8];
       load8(row + i, f);
@@ -142,7 +153,17 @@ __global__ void __launch_bounds__(1024) fp8_quant_token_kernel(uint8_t* __restri
   }
   __syncthreads();
   const float s = s_scale;
-  if (vec) {
+  if (keep) {
+    if (mine) {
+      uint32_t lo = 0, hi = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        lo |= (uint32_t)to_e4m3_div(kept[j], s) << (8 * j);
+        hi |= (uint32_t)to_e4m3_div(kept[4 + j], s) << (8 * j);
+      }
+      *reinterpret_cast<uint2*>(orow + threadIdx.x * 8) = make_uint2(lo, hi);
+    }
+  } else if (vec) {
     for (int i = threadIdx.x * 8; i < hidden; i += blockDim.x * 8) {     // second read of the row: L1 / L2 resident
       float f[8];
       load8(row + i, f);

@@ -19,11 +19,14 @@
 //   * epilogue warps tcgen05.ld their TMEM lane quadrant (lane = channel, column = token), apply the scales / bias,
 //     round once and store
 //   * k-split (decode shapes have few tiles: 4096 channels = 32 tiles on 148 SMs): the splits of a tile are the CTAs
-//     of one thread-block cluster (1, 1, S). After the main loop the pipeline buffers are idle, so every split PUSHES
-//     its fp32 partial rows into the shared memory of the split that owns the row (st.shared::cluster, rows
-//     interleaved over the splits), a cluster barrier publishes them, and each split sums ITS rows over the S slots in
-//     split order: deterministic, no global scratch (the op has no workspace argument), no atomics, and the output
-//     rows leave as 256-byte coalesced stores.
+//     of one thread-block cluster (1, 1, S) — co-resident by construction, so `barrier.cluster` is a rendezvous that
+//     cannot deadlock. Every split stores its 32-bit partial tile in its own slab of a caller-provided scratch
+//     [S, M, N] (L2-resident: 2 MB per slab at 256 x 2048), the barrier publishes the slabs, and each split reduces an
+//     interleaved 1/S share of the token rows over the slabs IN SPLIT ORDER, applies the scales and writes the rows as
+//     256-byte coalesced stores: deterministic, no atomics, no second kernel (the scheme of marlin_gemm.cu). A first
+//     version pushed the partials into the owner's shared memory with 4-byte st.shared::cluster stores: 4096 x 6144 at
+//     256 tokens took 112 us against 69 us for the un-split 4096 x 28672 (profiles/r02_bench_f_rows_first.json) —
+//     scattered 4-byte DSMEM stores are issued per thread, not per warp.
 #include "common.cuh"
 #include "tc5.cuh"
 
@@ -54,22 +57,12 @@ struct ScaledMMParams {
   int act_bytes;            // box_rows * 128
   int stages;
   int split_k, chunks_per_split;
+  uint32_t* scratch;        // [split_k, M, N] 32-bit partials (fp32, or s32 for int8); used when split_k > 1
 };
 
-__device__ __forceinline__ uint32_t sm_cluster_rank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
 __device__ __forceinline__ void sm_cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void st_remote_u32(uint32_t local_saddr, uint32_t cta_rank, uint32_t v) {
-  uint32_t remote;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_saddr), "r"(cta_rank));
-  asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(remote), "r"(v) : "memory");
-}
-
 template <typename T, int KIND>
 __global__ void __launch_bounds__(SM_THREADS, 1)
 scaled_mm_tc5_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_a,
@@ -157,31 +150,22 @@ scaled_mm_tc5_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
   }
 
   const int S = p.split_k;
-  const uint32_t rank = S > 1 ? sm_cluster_rank() : 0u;
-  const int rows_per = (toks + S - 1) / S;                      // token rows of this tile owned by one split
-  uint32_t* red = reinterpret_cast<uint32_t*>(tiles);           // [S slots][rows_per][128 ch] 32-bit partials (S > 1)
-
-  if (S > 1) {
-    // every split of the tile has finished reading its pipeline buffers before anyone pushes partials into them
-    if (warp >= 2) { mbar_wait(accum_full, 0); tc_fence_after(); }
-    __syncthreads();
-    sm_cluster_sync();
-  }
-
   if (warp >= 2) {
     // ===================== epilogue =====================
-    if (S == 1) { mbar_wait(accum_full, 0); tc_fence_after(); }
+    mbar_wait(accum_full, 0);
+    tc_fence_after();
     const int quad = warp & 3;                                   // TMEM lanes 32*quad .. +31 belong to this warp
     const int chl = quad * 32 + lane;
     const int ch = n_base + chl;
     const bool ch_ok = ch < p.N;
     T* cptr = reinterpret_cast<T*>(p.c);
     float bs = 0.f, bv = 0.f;
-    if (ch_ok) {
+    if (ch_ok && S == 1) {
       bs = p.b_scale_per_channel ? __ldg(p.b_scales + ch) : __ldg(p.b_scales);
       if (p.bias != nullptr) bv = to_f32<T>(reinterpret_cast<const T*>(p.bias)[ch]);
     }
     const bool has_bias = p.bias != nullptr;
+    uint32_t* slab = S > 1 ? p.scratch + (size_t)blockIdx.z * p.M * p.N : nullptr;
     for (int col0 = 0; col0 < n_mma; col0 += 32) {
       uint32_t v[32];
       tmem_ld32(tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)col0, v);
@@ -198,24 +182,19 @@ scaled_mm_tc5_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
             cptr[(size_t)(tok_base + col0 + t) * p.ldc + ch] = from_f32<T>(o);
           }
         }
-      } else {
+      } else if (ch_ok) {
 #pragma unroll
-        for (int t = 0; t < 32; ++t) {
-          const int tok = col0 + t;
-          if (tok < toks) {
-            const uint32_t owner = (uint32_t)(tok % S);
-            const uint32_t row = (uint32_t)(tok / S);
-            st_remote_u32(smem_u32(red + ((size_t)rank * rows_per + row) * SM_NT + chl), owner, v[t]);
-          }
-        }
+        for (int t = 0; t < 32; ++t)
+          if (col0 + t < toks) slab[(size_t)(tok_base + col0 + t) * p.N + ch] = v[t];
       }
     }
     tc_fence_before();
   }
 
   if (S > 1) {
+    __threadfence();                   // slab stores -> visible to the cluster's other SMs
     __syncthreads();
-    sm_cluster_sync();                 // all partial rows have landed in their owners' shared memory
+    sm_cluster_sync();
     if (warp >= 2) {
       const int chl = threadIdx.x - 64;                         // 128 epilogue threads = 128 channels: coalesced rows
       const int ch = n_base + chl;
@@ -224,15 +203,22 @@ scaled_mm_tc5_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
         const float bs = p.b_scale_per_channel ? __ldg(p.b_scales + ch) : __ldg(p.b_scales);
         const bool has_bias = p.bias != nullptr;
         const float bv = has_bias ? to_f32<T>(reinterpret_cast<const T*>(p.bias)[ch]) : 0.f;
-        for (int row = 0; (int)rank + row * S < toks; ++row) {
-          const int tok = (int)rank + row * S;
+        const size_t slab_elems = (size_t)p.M * p.N;
+        for (int tok = (int)blockIdx.z; tok < toks; tok += S) {
+          const uint32_t* src = p.scratch + (size_t)(tok_base + tok) * p.N + ch;
           float acc;
           if constexpr (KIND == SMK_FP8) {
             acc = 0.f;
-            for (int z = 0; z < S; ++z) acc += __uint_as_float(red[((size_t)z * rows_per + row) * SM_NT + chl]);   // split order
+            for (int z0 = 0; z0 < S; z0 += 4) {                 // four slab loads in flight, added in split order
+              float v4[4];
+#pragma unroll
+              for (int z = 0; z < 4; ++z) v4[z] = (z0 + z < S) ? __uint_as_float(__ldcg(src + (size_t)(z0 + z) * slab_elems)) : 0.f;
+#pragma unroll
+              for (int z = 0; z < 4; ++z) acc += v4[z];
+            }
           } else {
             int iacc = 0;
-            for (int z = 0; z < S; ++z) iacc += (int)red[((size_t)z * rows_per + row) * SM_NT + chl];
+            for (int z = 0; z < S; ++z) iacc += (int)__ldcg(src + (size_t)z * slab_elems);
             acc = (float)iacc;
           }
           const float as = p.a_scale_per_token ? __ldg(p.a_scales + tok_base + tok) : __ldg(p.a_scales);
@@ -289,12 +275,6 @@ static int launch_scaled_mm(const CUtensorMap& tw, const CUtensorMap& ta, Scaled
   p.stages = std::min(SM_MAX_STAGES, (SM_SMEM_TOTAL - SM_FIXED) / stage_bytes);
   B200_CHECK(p.stages >= 2, "scaled_mm: shared-memory plan leaves fewer than two pipeline stages");
   const size_t smem = (size_t)p.stages * stage_bytes + SM_FIXED;
-  // the k-split reduction reuses the pipeline buffers: [S][ceil(tokens / S)][128] 32-bit partials
-  if (p.split_k > 1) {
-    const int toks = std::min(p.M, SM_TOK);
-    const size_t need = (size_t)p.split_k * ((toks + p.split_k - 1) / p.split_k) * SM_NT * 4;
-    B200_CHECK(need <= (size_t)p.stages * stage_bytes, "scaled_mm: k-split reduction buffer does not fit");
-  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;
   cfg.blockDim = dim3(SM_THREADS, 1, 1);
@@ -329,7 +309,7 @@ extern "C" int b200_cutlass_scaled_mm_supports_fp8(int cuda_device_capability) {
 extern "C" int b200_cutlass_scaled_mm(void* out, const void* a, const void* b, const float* a_scales,
                                       const float* b_scales, const void* bias, int size_m, int size_n, int size_k,
                                       int64_t lda, int64_t ldb, int64_t ldc, int a_scales_numel, int b_scales_numel,
-                                      int ab_dtype, int out_dtype, int split_k, void* stream) {
+                                      int ab_dtype, int out_dtype, int split_k, void* workspace, void* stream) {
   B200_CHECK(ab_dtype == B200_AB_FP8_E4M3 || ab_dtype == B200_AB_INT8, "cutlass_scaled_mm: a and b must be float8_e4m3fn or int8");
   B200_CHECK(out_dtype == B200_F16 || out_dtype == B200_BF16, "cutlass_scaled_mm: out must be float16 or bfloat16");
   B200_CHECK(size_m >= 0 && size_n > 0 && size_k > 0, "cutlass_scaled_mm: invalid problem size");
@@ -357,9 +337,12 @@ extern "C" int b200_cutlass_scaled_mm(void* out, const void* a, const void* b, c
   const int chunks = (size_k + SM_KC - 1) / SM_KC;
   if (split_k <= 0) split_k = plan_scaled_mm_split(size_m, size_n, size_k);
   split_k = std::max(1, std::min(std::min(split_k, 8), chunks));
+  if (workspace == nullptr) split_k = 1;                    // no scratch: one CTA per tile walks the whole k range
   while (split_k > 1 && (split_k - 1) * ((chunks + split_k - 1) / split_k) >= chunks) --split_k;
   p.split_k = split_k;
   p.chunks_per_split = (chunks + split_k - 1) / split_k;
+  p.scratch = reinterpret_cast<uint32_t*>(workspace);
+  B200_CHECK(split_k == 1 || (reinterpret_cast<uintptr_t>(workspace) & 3) == 0, "scaled_mm workspace must be 4-byte aligned");
   dim3 grid((size_n + SM_NT - 1) / SM_NT, (size_m + SM_TOK - 1) / SM_TOK, split_k);
   cudaStream_t st = (cudaStream_t)stream;
   if (ab_dtype == B200_AB_FP8_E4M3) {

@@ -80,11 +80,16 @@ void cutlass_scaled_mm(torch::Tensor& c, torch::Tensor const& a, torch::Tensor c
   if (a.scalar_type() == at::kChar && b.scalar_type() == at::kChar) ab = B200_AB_INT8;
   TORCH_CHECK(ab >= 0, "cutlass_scaled_mm: a and b must both be float8_e4m3fn or both be int8");
   const at::cuda::OptionalCUDAGuard guard(device_of(a));
+  // k-split partial tiles: fp32 scratch from the caching allocator (safe under CUDA-graph capture); the reference op has
+  // no workspace argument to carry it
+  const int split = b200_scaled_mm_plan((int)a.size(0), (int)b.size(1), (int)a.size(1));
+  torch::Tensor ws;
+  if (split > 1) ws = torch::empty({(int64_t)split, a.size(0), b.size(1)}, torch::dtype(torch::kFloat32).device(a.device()));
   check(b200_cutlass_scaled_mm(c.data_ptr(), a.data_ptr(), b.data_ptr(), a_scales.data_ptr<float>(),
                                b_scales.data_ptr<float>(), bias ? bias->data_ptr() : nullptr, (int)a.size(0),
                                (int)b.size(1), (int)a.size(1), a.stride(0), b.stride(1), c.stride(0),
-                               (int)a_scales.numel(), (int)b_scales.numel(), ab, dtype_code(c, "cutlass_scaled_mm"), 0,
-                               cur_stream()));
+                               (int)a_scales.numel(), (int)b_scales.numel(), ab, dtype_code(c, "cutlass_scaled_mm"), split,
+                               split > 1 ? ws.data_ptr() : nullptr, cur_stream()));
 }
 void cutlass_scaled_mm_azp(torch::Tensor& c, torch::Tensor const& a, torch::Tensor const& b, torch::Tensor const& a_scales,
                            torch::Tensor const& b_scales, torch::Tensor const& azp_adj,

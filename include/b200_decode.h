@@ -317,15 +317,17 @@ int b200_dynamic_per_token_scaled_fp8_quant(void* out, const void* input, float*
  * out[M,N] = T(a_scales[m|0] * (b_scales[n|0] * sum_k a[m,k] b[k,n]) + bias[n]); a [M,K] row-major (row stride lda),
  * b [K,N] COLUMN-major (column stride ldb, i.e. the [N,K] weight), both float8_e4m3fn or both int8 (ab_dtype);
  * out fp16 / bf16 (out_dtype), row stride ldc; a_scales / b_scales fp32 with 1 or M / N entries; bias T [N] or NULL.
- * split_k <= 0 lets the library choose (b200_scaled_mm_plan). tcgen05 kind::f8f6f4 / kind::i8, no workspace. Not
- * implemented (clear error from the torch op): the asymmetric variant cutlass_scaled_mm_azp. */
+ * split_k <= 0 lets the library choose; workspace = fp32 scratch of b200_scaled_mm_plan(M, N, K) * M * N elements for
+ * the k-split partial tiles (no initialisation needed; NULL forces one CTA per tile). The reference op has no workspace
+ * argument: the torch shim allocates it from the caching allocator (graph-capturable). tcgen05 kind::f8f6f4 / kind::i8.
+ * Not implemented (clear error from the torch op): the asymmetric variant cutlass_scaled_mm_azp. */
 enum { B200_AB_FP8_E4M3 = 0, B200_AB_INT8 = 1 };
 int b200_cutlass_scaled_mm_supports_fp8(int cuda_device_capability);
 int b200_scaled_mm_plan(int size_m, int size_n, int size_k);
 int b200_cutlass_scaled_mm(void* out, const void* a, const void* b, const float* a_scales, const float* b_scales,
                            const void* bias, int size_m, int size_n, int size_k, int64_t lda, int64_t ldb,
                            int64_t ldc, int a_scales_numel, int b_scales_numel, int ab_dtype, int out_dtype,
-                           int split_k, void* stream);
+                           int split_k, void* workspace, void* stream);
 
 /* ---- sampling --------------------------------------------------------------------------------
  * replaces sampling_from_probs, top_k_ / top_p_ / min_p_ / top_k_top_p_sampling_from_probs, top_p_renorm_prob,

@@ -248,7 +248,7 @@ def test_scaled_mm_vs_oracle(ops, kind, out_dtype, mnk, scales):
 
 
 def test_scaled_mm_k_splits_are_bit_identical(cabi):
-    """Every split plan through the C ABI (cluster of S CTAs, partial rows pushed over DSMEM) gives the same bits for
+    """Every split plan through the C ABI (cluster of S CTAs, partial tiles in the fp32 scratch) gives the same bits for
     int8 (integer partial sums) and fp8 results within fp32 re-association of the unsplit result; repeated launches of
     one plan are bit-identical (deterministic reduction order)."""
     import ctypes
@@ -259,11 +259,12 @@ def test_scaled_mm_k_splits_are_bit_identical(cabi):
         sa = torch.tensor([1.0], device=DEV)
         sb = torch.tensor([1.0 / 4096 if kind == "fp8" else 1.0 / (4096 * 64)], device=DEV)
         outs = {}
+        scratch = torch.empty(8, M, N, dtype=torch.float32, device=DEV)
         for split in (1, 2, 3, 4, 8):
             o = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
             for rep in range(2):
                 rc = cabi.b200_cutlass_scaled_mm(o.data_ptr(), ad.data_ptr(), wd.data_ptr(), sa.data_ptr(), sb.data_ptr(),
-                                                 None, M, N, K, K, K, N, 1, 1, code, 2, split,
+                                                 None, M, N, K, K, K, N, 1, 1, code, 2, split, scratch.data_ptr(),
                                                  ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
                 assert rc == 0, cabi.b200_last_error()
                 torch.cuda.synchronize()
@@ -315,8 +316,10 @@ def test_sampling_from_probs_vs_oracle(ops, V):
     assert sure.sum() >= B - 4
     assert (ids[sure] == ref[sure]).all(), (ids, ref, margins)
     cdf = np.cumsum(p.numpy().astype(np.float64), axis=1)
-    for b in np.nonzero(~sure)[0]:                              # borderline rows: still a neighbour of the crossing
-        assert abs(cdf[b, ids[b]] - u[b].item()) < 1e-4
+    for b in np.nonzero(~sure)[0]:                              # borderline rows: still the crossing, up to fp32 rounding
+        i = int(ids[b])
+        lo = cdf[b, i - 1] if i > 0 else 0.0
+        assert (lo - 1e-5 <= u[b].item() < cdf[b, i] + 1e-5) or i == V - 1
 
 
 @pytest.mark.parametrize("mode", ["top_k", "top_p", "min_p", "top_k_top_p"])
