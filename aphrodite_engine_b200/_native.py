@@ -80,6 +80,7 @@ SIGNATURES = {
     "b200_dynamic_per_token_scaled_fp8_quant": [c_void_p] * 4 + [c_int] * 3 + [c_void_p],
     "b200_cutlass_scaled_mm_supports_fp8": [c_int],
     "b200_scaled_mm_plan": [c_int] * 3,
+    "b200_scaled_mm_set_tile": [c_int],
     "b200_cutlass_scaled_mm": [c_void_p] * 6 + [c_int] * 3 + [c_int64] * 3 + [c_int] * 5 + [c_void_p] * 2,
     "b200_sampling_from_probs": [c_void_p] * 3 + [c_int] * 3 + [c_void_p],
     "b200_rejection_sampling_from_probs": [c_int] + [c_void_p] * 5 + [c_int, c_void_p, c_float] + [c_int] * 4 +

@@ -43,6 +43,7 @@ struct PrefillParams {
   int64_t kc_block_stride, kc_head_stride, vc_block_stride, vc_head_stride;   // elements of the cache type
   int64_t bt_stride;
   int num_heads, num_kv_heads, block_size, x;
+  int bs_shift, x_shift;     // log2 of block_size / x (both powers of two): the tile loaders never divide
   int sliding_window;
   float scale, k_scale, v_scale;
 };
@@ -82,7 +83,7 @@ __device__ __forceinline__ uint4 load_cache8(const void* src, float scale) {
 }
 
 template <typename T, int DT, int KV>
-__global__ void __launch_bounds__(PF_THREADS) prefill_attention_kernel(const PrefillParams p) {
+__global__ void __launch_bounds__(PF_THREADS, (DT == 8 ? 3 : 1)) prefill_attention_kernel(const PrefillParams p) {
   constexpr int D = DT * 16;
   constexpr int KSTR = D + 8;                                  // elements per K / new-V row (+16 B pad)
   constexpr int K_TILE = PF_BN * KSTR;                         // elements
@@ -138,61 +139,75 @@ __global__ void __launch_bounds__(PF_THREADS) prefill_attention_kernel(const Pre
   const T* kn = reinterpret_cast<const T*>(p.k) + (size_t)kvh * p.k_stride_h;
   const T* vn = reinterpret_cast<const T*>(p.v) + (size_t)kvh * p.v_stride_h;
 
+  // Tile loaders. All per-thread piece coordinates are fixed outside the tile loop (128 threads, pieces strided by
+  // 128): a thread always serves the same token (K) / the same 8-token group (V) of a tile, so a tile costs it ONE
+  // block-table lookup per operand and shift / add addressing (the first version recomputed div / mod by the runtime
+  // block size for every 16-byte piece: 27 % IMAD + 14 % ISETP + the IABS / MUFU.RCP of emulated division against 5 % HMMA
+  // in the executed-instruction mix, profiles/r02_prefill_attention_first_ncu.txt).
+  const int bs_shift = p.bs_shift, bs_mask = BS - 1, x_shift = p.x_shift, x_mask = p.x - 1;
+  const int k_tl = tid & (PF_BN - 1), k_c0 = tid >> 6;          // ctx K: token of the tile, first chunk (chunks step 2)
+  const int v_tg = tid & 7, v_d0 = tid >> 3;                    // ctx V: 8-token group of the tile, first head-dim row (rows step 16)
   auto load_tile = [&](int tile, int stage) {
     T* ks = sm + (size_t)stage * (K_TILE + V_TILE);
     T* vs = ks + K_TILE;
     if (tile < n_ctx) {
       const int tile_start = tile * PF_BN;
-      // K: piece (chunk c of 8 head-dim elements, token tl) = half or all of one x-run of the paged layout
-      for (int i = tid; i < PF_BN * CH; i += PF_THREADS) {
-        const int tl = i % PF_BN, c = i / PF_BN;
-        const int pos = tile_start + tl;
+      {
+        // K: piece (chunk c of 8 head-dim elements, token) = half or all of one x-run of the paged layout
+        const int pos = tile_start + k_tl;
         const bool valid = pos < ctx_len;
-        const int blk = valid ? bt[pos / BS] : 0;
-        const int e0 = c * 8;
-        const CT* src = kc + (size_t)blk * p.kc_block_stride + ((size_t)(e0 / p.x) * BS + (valid ? pos % BS : 0)) * p.x + (e0 % p.x);
-        T* dst = ks + tl * KSTR + c * 8;
-        if constexpr (KV == B200_KV_AUTO) {
-          cp_async16_zfill(smem_u32(dst), src, valid);
-        } else {
-          *reinterpret_cast<uint4*>(dst) = valid ? load_cache8<T, KV>(src, p.k_scale) : make_uint4(0, 0, 0, 0);
+        const int blk = valid ? bt[pos >> bs_shift] : 0;
+        // chunk c = k_c0 + 2r covers elements 8c .. 8c+7: run (8c >> x_shift), offset (8c & x_mask); stepping c by 2 advances
+        // 16 elements = 16 << bs_shift cache elements whatever x is
+        const int e00 = k_c0 * 8;
+        const CT* src = kc + (size_t)blk * p.kc_block_stride + (size_t)((valid ? pos & bs_mask : 0) << x_shift) +
+                        ((size_t)(e00 >> x_shift) << (bs_shift + x_shift)) + (e00 & x_mask);
+        const size_t kstep = (size_t)16 << bs_shift;
+        T* dst = ks + k_tl * KSTR + k_c0 * 8;
+#pragma unroll
+        for (int r = 0; r < CH / 2; ++r) {
+          if constexpr (KV == B200_KV_AUTO) {
+            cp_async16_zfill(smem_u32(dst + r * 16), src + r * kstep, valid);
+          } else {
+            *reinterpret_cast<uint4*>(dst + r * 16) = valid ? load_cache8<T, KV>(src + r * kstep, p.k_scale) : make_uint4(0, 0, 0, 0);
+          }
         }
       }
-      // V: piece = 8 consecutive tokens of one head-dim row inside one cache block; consecutive threads walk the
-      // contiguous [D][BS] region of a block
-      const int ppb = BS / 8;                                  // pieces per row per block
-      const int per_blk = D * ppb;
-      for (int i = tid; i < D * (PF_BN / 8); i += PF_THREADS) {
-        const int bi = i / per_blk, r = i % per_blk;
-        const int d = r / ppb, tp = r % ppb;
-        const int tl0 = bi * BS + tp * 8;
-        const int pos0 = tile_start + tl0;
-        T* dst = vs + d * PF_VT_STRIDE + tl0;
-        const int nvalid = ctx_len - pos0;                      // tokens of the piece inside the context
-        if (nvalid <= 0) {
-          *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
-          continue;
-        }
-        const int blk = bt[pos0 / BS];
-        const CT* src = vc + (size_t)blk * p.vc_block_stride + (size_t)d * BS + (pos0 % BS);
-        if (nvalid >= 8) {
-          if constexpr (KV == B200_KV_AUTO) cp_async16_zfill(smem_u32(dst), src, true);
-          else *reinterpret_cast<uint4*>(dst) = load_cache8<T, KV>(src, p.v_scale);
-        } else {
-          // partially valid piece: the slots beyond the context may hold anything (NaNs included) and 0 * NaN = NaN in
-          // the MMA, so they are zeroed (the reference's masked load, prefix_prefill.py:163-165)
-          uint4 v = load_cache8<T, KV>(src, p.v_scale);
-          uint16_t* e = reinterpret_cast<uint16_t*>(&v);
+      {
+        // V: piece = 8 consecutive tokens of one head-dim row inside one cache block
+        const int pos0 = tile_start + v_tg * 8;
+        const int nvalid = ctx_len - pos0;                      // tokens of the group inside the context
+        const int blk = nvalid > 0 ? bt[pos0 >> bs_shift] : 0;
+        const CT* vb = vc + (size_t)blk * p.vc_block_stride + (pos0 & bs_mask) + ((size_t)v_d0 << bs_shift);
+        const size_t vstep = (size_t)16 << bs_shift;
+        T* dst = vs + v_d0 * PF_VT_STRIDE + v_tg * 8;
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (j >= nvalid) e[j] = 0;
-          *reinterpret_cast<uint4*>(dst) = v;
+        for (int r = 0; r < D / 16; ++r) {
+          const CT* src = vb + r * vstep;
+          T* d8 = dst + r * 16 * PF_VT_STRIDE;
+          if (nvalid >= 8) {
+            if constexpr (KV == B200_KV_AUTO) cp_async16_zfill(smem_u32(d8), src, true);
+            else *reinterpret_cast<uint4*>(d8) = load_cache8<T, KV>(src, p.v_scale);
+          } else if (nvalid <= 0) {
+            *reinterpret_cast<uint4*>(d8) = make_uint4(0, 0, 0, 0);
+          } else {
+            // partially valid group: the slots beyond the context may hold anything (NaNs included) and 0 * NaN = NaN in
+            // the MMA, so they are zeroed (the reference's masked load, prefix_prefill.py:163-165)
+            uint4 v = load_cache8<T, KV>(src, p.v_scale);
+            uint16_t* e = reinterpret_cast<uint16_t*>(&v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (j >= nvalid) e[j] = 0;
+            *reinterpret_cast<uint4*>(d8) = v;
+          }
         }
       }
     } else {
       const int tile_start = (tile - n_ctx) * PF_BN;
-      for (int i = tid; i < PF_BN * CH; i += PF_THREADS) {
-        const int tl = i / CH, c = i % CH;
+#pragma unroll
+      for (int r = 0; r < PF_BN * CH / PF_THREADS; ++r) {
+        const int i = tid + r * PF_THREADS;
+        const int tl = i / CH, c = i % CH;                       // CH is a compile-time constant
         const int pos = tile_start + tl;
         const bool valid = pos < q_len;
         const size_t tok = (size_t)(start + (valid ? pos : 0));
@@ -239,21 +254,34 @@ __global__ void __launch_bounds__(PF_THREADS) prefill_attention_kernel(const Pre
 
     // ---- scale, bias, masks, online softmax ---------------------------------------------------------------------
     float mx[2] = {-INFINITY, -INFINITY};
+    // tiles that lie entirely inside the context / strictly below the causal diagonal need no mask at all
+    const bool plain = !has_alibi && sw <= 0 && (is_ctx ? (tile_start + PF_BN <= ctx_len) : (tile - n_ctx < mt));
+    if (plain) {
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
+      for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int row = (e < 2) ? row0 : row1;
-        const int col = tile_start + nt * 8 + 2 * t4 + (e & 1);
-        const int qpos = ctx_len + row;
-        const int kpos = is_ctx ? col : ctx_len + col;
-        const bool valid = is_ctx ? (col < ctx_len) : (col <= row && col < q_len);
-        float v = s[nt][e] * scale2;
-        if (has_alibi) v += slope2 * (float)(kpos - qpos);
-        if (sw > 0 && qpos - kpos >= sw) v = -10000.f * LOG2E;
-        if (!valid) v = -INFINITY;
-        s[nt][e] = v;
-        mx[e >> 1] = fmaxf(mx[e >> 1], v);
+        for (int e = 0; e < 4; ++e) {
+          s[nt][e] *= scale2;
+          mx[e >> 1] = fmaxf(mx[e >> 1], s[nt][e]);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int row = (e < 2) ? row0 : row1;
+          const int col = tile_start + nt * 8 + 2 * t4 + (e & 1);
+          const int qpos = ctx_len + row;
+          const int kpos = is_ctx ? col : ctx_len + col;
+          const bool valid = is_ctx ? (col < ctx_len) : (col <= row && col < q_len);
+          float v = s[nt][e] * scale2;
+          if (has_alibi) v += slope2 * (float)(kpos - qpos);
+          if (sw > 0 && qpos - kpos >= sw) v = -10000.f * LOG2E;
+          if (!valid) v = -INFINITY;
+          s[nt][e] = v;
+          mx[e >> 1] = fmaxf(mx[e >> 1], v);
+        }
       }
     }
     float alpha[2], msafe[2];
@@ -412,6 +440,8 @@ extern "C" int b200_context_attention_fwd(
   p.kc_block_stride = kc_block_stride; p.kc_head_stride = kc_head_stride;
   p.vc_block_stride = vc_block_stride; p.vc_head_stride = vc_head_stride; p.bt_stride = bt_stride;
   p.num_heads = num_heads; p.num_kv_heads = num_kv_heads; p.block_size = block_size; p.x = x;
+  p.bs_shift = block_size == 8 ? 3 : block_size == 16 ? 4 : block_size == 32 ? 5 : 6;
+  p.x_shift = x == 8 ? 3 : 4;
   p.sliding_window = sliding_window > 0 ? sliding_window : 0;
   p.scale = scale; p.k_scale = k_scale; p.v_scale = v_scale;
   dim3 grid((max_query_len + PF_BM - 1) / PF_BM, num_heads, batch);

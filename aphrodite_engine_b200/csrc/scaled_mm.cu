@@ -63,30 +63,37 @@ struct ScaledMMParams {
 __device__ __forceinline__ void sm_cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-template <typename T, int KIND>
+// NSUB = 128-channel sub-tiles per CTA (1 or 2). With 2, one activation tile feeds two weight sub-tiles (two TMEM
+// accumulators): the activation tile is the larger half of a stage at 256 tokens and every CTA re-reads it from L2, and
+// the first version (NSUB = 1 only) ran at the L2 -> SM fabric rate, not at the tensor or DRAM rate (ncu: 352 MB through
+// the crossbar for 119 MB of DRAM reads, 5.7 TB/s, tensor pipe 22 % of elapsed; profiles/r02_scaled_mm_fp8_m256_first_ncu.txt).
+template <typename T, int KIND, int NSUB>
 __global__ void __launch_bounds__(SM_THREADS, 1)
 scaled_mm_tc5_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_a,
                      const ScaledMMParams p) {
+  constexpr int CTA_CH = SM_NT * NSUB;
+  constexpr int W_BYTES = CTA_CH * SM_KC;
   extern __shared__ uint8_t sm_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sm_smem_raw) + 1023) & ~(uintptr_t)1023);
   const int NS = p.stages;
-  const int stage_bytes = SM_W_BYTES + p.act_bytes;
-  uint8_t* tiles = smem;                                     // [NS][ W tile 16 KB | activation tile act_bytes ]
+  const int stage_bytes = W_BYTES + p.act_bytes;
+  uint8_t* tiles = smem;                                     // [NS][ W tile (NSUB x 16 KB) | activation tile act_bytes ]
   uint64_t* full = reinterpret_cast<uint64_t*>(tiles + (size_t)NS * stage_bytes);
   uint64_t* empty = full + SM_MAX_STAGES;
   uint64_t* accum_full = empty + SM_MAX_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_base = blockIdx.x * SM_NT;
+  const int n_base = blockIdx.x * CTA_CH;
   const int tok_base = blockIdx.y * SM_TOK;
   const int toks = min(SM_TOK, p.M - tok_base);
   const int n_mma = max(16, (toks + 15) & ~15);
   const int total_chunks = (p.K + SM_KC - 1) / SM_KC;
   const int chunk0 = blockIdx.z * p.chunks_per_split;
   const int nchunks = min(p.chunks_per_split, total_chunks - chunk0);     // >= 1 by construction of the split plan
-  uint32_t tmem_cols = 32;
-  while ((int)tmem_cols < n_mma) tmem_cols <<= 1;
+  uint32_t acc_stride = 32;                                   // TMEM columns between the sub-tiles' accumulators
+  while ((int)acc_stride < n_mma) acc_stride <<= 1;
+  const uint32_t tmem_cols = acc_stride * NSUB;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < SM_MAX_STAGES; ++i) {
@@ -107,13 +114,13 @@ scaled_mm_tc5_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
     if (elect_one()) {
       int s = 0;
       uint32_t use = 0;
-      const uint32_t tx_bytes = (uint32_t)SM_W_BYTES + (uint32_t)p.box_rows * 128u;   // TMA always moves the full boxes
+      const uint32_t tx_bytes = (uint32_t)W_BYTES + (uint32_t)p.box_rows * 128u;   // TMA always moves the full boxes
       for (int c = 0; c < nchunks; ++c) {
         if (use > 0) mbar_wait(&empty[s], (use - 1) & 1u);
         uint8_t* st = tiles + (size_t)s * stage_bytes;
         mbar_arrive_expect_tx(&full[s], tx_bytes);
         tma_load_2d(st, &tmap_w, &full[s], (chunk0 + c) * SM_KC, n_base);
-        tma_load_2d(st + SM_W_BYTES, &tmap_a, &full[s], (chunk0 + c) * SM_KC, tok_base);
+        tma_load_2d(st + W_BYTES, &tmap_a, &full[s], (chunk0 + c) * SM_KC, tok_base);
         if (++s == NS) { s = 0; ++use; }
       }
     }
@@ -132,15 +139,21 @@ scaled_mm_tc5_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
         mbar_wait(&full[s], use & 1u);
         tc_fence_after();
         const uint32_t st = smem_u32(tiles + (size_t)s * stage_bytes);
-        const uint64_t a_desc = make_sw128_desc(st);                   // weights: UMMA "A" (M = channels)
-        const uint64_t b_desc = make_sw128_desc(st + SM_W_BYTES);      // activations: UMMA "B" (N = tokens)
+        const uint64_t b_desc = make_sw128_desc(st + W_BYTES);         // activations: UMMA "B" (N = tokens)
 #pragma unroll
         for (int ks = 0; ks < SM_KC / 32; ++ks) {
-          // 32 k = 32 bytes further inside the 128-byte swizzle row = +2 in the descriptor's (address >> 4) field
-          if constexpr (KIND == SMK_FP8)
-            umma_f8(tmem_d, a_desc + (uint64_t)(2 * ks), b_desc + (uint64_t)(2 * ks), idesc, (c > 0 || ks > 0) ? 1u : 0u);
-          else
-            umma_i8(tmem_d, a_desc + (uint64_t)(2 * ks), b_desc + (uint64_t)(2 * ks), idesc, (c > 0 || ks > 0) ? 1u : 0u);
+#pragma unroll
+          for (int j = 0; j < NSUB; ++j) {
+            // weights of sub-tile j: UMMA "A" (M = 128 channels), rows j*128.. of the stage's W tile (128 B per row)
+            const uint64_t a_desc = make_sw128_desc(st + (uint32_t)j * (SM_NT * SM_KC));
+            // 32 k = 32 bytes further inside the 128-byte swizzle row = +2 in the descriptor's (address >> 4) field
+            if constexpr (KIND == SMK_FP8)
+              umma_f8(tmem_d + (uint32_t)j * acc_stride, a_desc + (uint64_t)(2 * ks), b_desc + (uint64_t)(2 * ks), idesc,
+                      (c > 0 || ks > 0) ? 1u : 0u);
+            else
+              umma_i8(tmem_d + (uint32_t)j * acc_stride, a_desc + (uint64_t)(2 * ks), b_desc + (uint64_t)(2 * ks), idesc,
+                      (c > 0 || ks > 0) ? 1u : 0u);
+          }
         }
         umma_commit(&empty[s]);          // frees stage s when these MMAs retire
         if (++s == NS) { s = 0; ++use; }
@@ -155,37 +168,39 @@ scaled_mm_tc5_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
     mbar_wait(accum_full, 0);
     tc_fence_after();
     const int quad = warp & 3;                                   // TMEM lanes 32*quad .. +31 belong to this warp
-    const int chl = quad * 32 + lane;
-    const int ch = n_base + chl;
-    const bool ch_ok = ch < p.N;
     T* cptr = reinterpret_cast<T*>(p.c);
-    float bs = 0.f, bv = 0.f;
-    if (ch_ok && S == 1) {
-      bs = p.b_scale_per_channel ? __ldg(p.b_scales + ch) : __ldg(p.b_scales);
-      if (p.bias != nullptr) bv = to_f32<T>(reinterpret_cast<const T*>(p.bias)[ch]);
-    }
     const bool has_bias = p.bias != nullptr;
     uint32_t* slab = S > 1 ? p.scratch + (size_t)blockIdx.z * p.M * p.N : nullptr;
-    for (int col0 = 0; col0 < n_mma; col0 += 32) {
-      uint32_t v[32];
-      tmem_ld32(tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)col0, v);
-      if (S == 1) {
-        float as_l = 1.f;
-        if (col0 + lane < toks) as_l = p.a_scale_per_token ? __ldg(p.a_scales + tok_base + col0 + lane) : __ldg(p.a_scales);
 #pragma unroll
-        for (int t = 0; t < 32; ++t) {
-          const float as = __shfl_sync(0xffffffffu, as_l, t);
-          if (ch_ok && col0 + t < toks) {
-            const float acc = KIND == SMK_FP8 ? __uint_as_float(v[t]) : (float)(int)v[t];
-            const float tmp = bs * acc;
-            const float o = has_bias ? fmaf(as, tmp, bv) : as * tmp;
-            cptr[(size_t)(tok_base + col0 + t) * p.ldc + ch] = from_f32<T>(o);
+    for (int j = 0; j < NSUB; ++j) {
+      const int ch = n_base + j * SM_NT + quad * 32 + lane;
+      const bool ch_ok = ch < p.N;
+      float bs = 0.f, bv = 0.f;
+      if (ch_ok && S == 1) {
+        bs = p.b_scale_per_channel ? __ldg(p.b_scales + ch) : __ldg(p.b_scales);
+        if (has_bias) bv = to_f32<T>(reinterpret_cast<const T*>(p.bias)[ch]);
+      }
+      for (int col0 = 0; col0 < n_mma; col0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)j * acc_stride + (uint32_t)col0, v);
+        if (S == 1) {
+          float as_l = 1.f;
+          if (col0 + lane < toks) as_l = p.a_scale_per_token ? __ldg(p.a_scales + tok_base + col0 + lane) : __ldg(p.a_scales);
+#pragma unroll
+          for (int t = 0; t < 32; ++t) {
+            const float as = __shfl_sync(0xffffffffu, as_l, t);
+            if (ch_ok && col0 + t < toks) {
+              const float acc = KIND == SMK_FP8 ? __uint_as_float(v[t]) : (float)(int)v[t];
+              const float tmp = bs * acc;
+              const float o = has_bias ? fmaf(as, tmp, bv) : as * tmp;
+              cptr[(size_t)(tok_base + col0 + t) * p.ldc + ch] = from_f32<T>(o);
+            }
           }
-        }
-      } else if (ch_ok) {
+        } else if (ch_ok) {
 #pragma unroll
-        for (int t = 0; t < 32; ++t)
-          if (col0 + t < toks) slab[(size_t)(tok_base + col0 + t) * p.N + ch] = v[t];
+          for (int t = 0; t < 32; ++t)
+            if (col0 + t < toks) slab[(size_t)(tok_base + col0 + t) * p.N + ch] = v[t];
+        }
       }
     }
     tc_fence_before();
@@ -195,37 +210,67 @@ scaled_mm_tc5_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
     __threadfence();                   // slab stores -> visible to the cluster's other SMs
     __syncthreads();
     sm_cluster_sync();
-    if (warp >= 2) {
-      const int chl = threadIdx.x - 64;                         // 128 epilogue threads = 128 channels: coalesced rows
-      const int ch = n_base + chl;
-      if (ch < p.N) {
-        T* cptr = reinterpret_cast<T*>(p.c);
-        const float bs = p.b_scale_per_channel ? __ldg(p.b_scales + ch) : __ldg(p.b_scales);
-        const bool has_bias = p.bias != nullptr;
-        const float bv = has_bias ? to_f32<T>(reinterpret_cast<const T*>(p.bias)[ch]) : 0.f;
-        const size_t slab_elems = (size_t)p.M * p.N;
-        for (int tok = (int)blockIdx.z; tok < toks; tok += S) {
-          const uint32_t* src = p.scratch + (size_t)(tok_base + tok) * p.N + ch;
-          float acc;
-          if constexpr (KIND == SMK_FP8) {
-            acc = 0.f;
-            for (int z0 = 0; z0 < S; z0 += 4) {                 // four slab loads in flight, added in split order
-              float v4[4];
+    // Reduction: this split owns token rows z, z + S, ...; every warp of the CTA takes rows of its own (row loads of
+    // different warps overlap — the first version walked the rows with all threads in lock step, one L2 round trip per
+    // row: 98 us on 4096 x 6144), a lane owns 4 adjacent channels (16-byte slab loads, 8-byte output stores), slabs are
+    // added in split order.
+    T* cptr = reinterpret_cast<T*>(p.c);
+    const bool has_bias = p.bias != nullptr;
+    const size_t slab_elems = (size_t)p.M * p.N;
+    constexpr int NWARPS = SM_THREADS / 32;
 #pragma unroll
-              for (int z = 0; z < 4; ++z) v4[z] = (z0 + z < S) ? __uint_as_float(__ldcg(src + (size_t)(z0 + z) * slab_elems)) : 0.f;
+    for (int cb = 0; cb < CTA_CH; cb += 128) {
+      const int ch = n_base + cb + lane * 4;
+      if (ch >= p.N) continue;
+      float bsv[4], bvv[4] = {0.f, 0.f, 0.f, 0.f};
+      if (p.b_scale_per_channel) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(p.b_scales + ch));
+        bsv[0] = t.x; bsv[1] = t.y; bsv[2] = t.z; bsv[3] = t.w;
+      } else {
+        bsv[0] = bsv[1] = bsv[2] = bsv[3] = __ldg(p.b_scales);
+      }
+      if (has_bias) {
+        const uint2 t = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const T*>(p.bias) + ch));
+        const T* tb = reinterpret_cast<const T*>(&t);
 #pragma unroll
-              for (int z = 0; z < 4; ++z) acc += v4[z];
+        for (int i = 0; i < 4; ++i) bvv[i] = to_f32<T>(tb[i]);
+      }
+      for (int tok = (int)blockIdx.z + S * warp; tok < toks; tok += S * NWARPS) {
+        const uint32_t* src = p.scratch + (size_t)(tok_base + tok) * p.N + ch;
+        float acc[4];
+        if constexpr (KIND == SMK_FP8) {
+          acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+          for (int z0 = 0; z0 < S; z0 += 4) {                   // four slab loads in flight, added in split order
+            uint4 v4[4];
+#pragma unroll
+            for (int z = 0; z < 4; ++z)
+              v4[z] = (z0 + z < S) ? __ldcg(reinterpret_cast<const uint4*>(src + (size_t)(z0 + z) * slab_elems)) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+            for (int z = 0; z < 4; ++z) {
+              acc[0] += __uint_as_float(v4[z].x); acc[1] += __uint_as_float(v4[z].y);
+              acc[2] += __uint_as_float(v4[z].z); acc[3] += __uint_as_float(v4[z].w);
             }
-          } else {
-            int iacc = 0;
-            for (int z = 0; z < S; ++z) iacc += (int)__ldcg(src + (size_t)z * slab_elems);
-            acc = (float)iacc;
           }
-          const float as = p.a_scale_per_token ? __ldg(p.a_scales + tok_base + tok) : __ldg(p.a_scales);
-          const float tmp = bs * acc;
-          const float o = has_bias ? fmaf(as, tmp, bv) : as * tmp;
-          cptr[(size_t)(tok_base + tok) * p.ldc + ch] = from_f32<T>(o);
+        } else {
+          int ia[4] = {0, 0, 0, 0};
+          for (int z = 0; z < S; ++z) {
+            const uint4 v = __ldcg(reinterpret_cast<const uint4*>(src + (size_t)z * slab_elems));
+            ia[0] += (int)v.x; ia[1] += (int)v.y; ia[2] += (int)v.z; ia[3] += (int)v.w;
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) acc[i] = (float)ia[i];
         }
+        const float as = p.a_scale_per_token ? __ldg(p.a_scales + tok_base + tok) : __ldg(p.a_scales);
+        float o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float tmp = bsv[i] * acc[i];
+          o[i] = has_bias ? fmaf(as, tmp, bvv[i]) : as * tmp;
+        }
+        uint2 packed;
+        packed.x = pack2<T>(o[0], o[1]);
+        packed.y = pack2<T>(o[2], o[3]);
+        *reinterpret_cast<uint2*>(cptr + (size_t)(tok_base + tok) * p.ldc + ch) = packed;
       }
     }
   }
@@ -251,9 +296,19 @@ static int encode_u8_map(CUtensorMap* tmap, const void* base, int64_t rows, int 
   return 0;
 }
 
+// channels per CTA: 256 (two sub-tiles share one activation tile) whenever the matrix has more than one 128-channel
+// tile; b200_scaled_mm_set_tile() overrides for A-B measurement (0 = auto, 1 = 128, 2 = 256)
+static thread_local int g_smm_tile = 0;
+static int scaled_mm_nsub(int N) {
+  if (g_smm_tile == 1) return 1;
+  if (g_smm_tile == 2) return 2;
+  return N > SM_NT ? 2 : 1;
+}
+
 // k-splits of one tile: enough to fill one wave of the SMs, at least 4 chunks (512 k) each, at most 8 (portable cluster)
 static int plan_scaled_mm_split(int M, int N, int K) {
-  const int tiles = ((N + SM_NT - 1) / SM_NT) * ((M + SM_TOK - 1) / SM_TOK);
+  const int cta_ch = SM_NT * scaled_mm_nsub(N);
+  const int tiles = ((N + cta_ch - 1) / cta_ch) * ((M + SM_TOK - 1) / SM_TOK);
   const int chunks = (K + SM_KC - 1) / SM_KC;
   int split = std::min(std::min(num_sms() / std::max(tiles, 1), chunks / 4), 8);
   if (split < 1) split = 1;
@@ -261,9 +316,9 @@ static int plan_scaled_mm_split(int M, int N, int K) {
   return split;
 }
 
-template <typename T, int KIND>
-static int launch_scaled_mm(const CUtensorMap& tw, const CUtensorMap& ta, ScaledMMParams& p, dim3 grid, cudaStream_t st) {
-  auto kern = scaled_mm_tc5_kernel<T, KIND>;
+template <typename T, int KIND, int NSUB>
+static int launch_scaled_mm_n(const CUtensorMap& tw, const CUtensorMap& ta, ScaledMMParams& p, dim3 grid, cudaStream_t st) {
+  auto kern = scaled_mm_tc5_kernel<T, KIND, NSUB>;
   static thread_local uint64_t attr_done = 0;
   int dev = 0;
   B200_CUDA_OK(cudaGetDevice(&dev));
@@ -271,7 +326,7 @@ static int launch_scaled_mm(const CUtensorMap& tw, const CUtensorMap& ta, Scaled
     B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_SMEM_TOTAL));
     attr_done |= 1ull << (dev & 63);
   }
-  const int stage_bytes = SM_W_BYTES + p.act_bytes;
+  const int stage_bytes = SM_W_BYTES * NSUB + p.act_bytes;
   p.stages = std::min(SM_MAX_STAGES, (SM_SMEM_TOTAL - SM_FIXED) / stage_bytes);
   B200_CHECK(p.stages >= 2, "scaled_mm: shared-memory plan leaves fewer than two pipeline stages");
   const size_t smem = (size_t)p.stages * stage_bytes + SM_FIXED;
@@ -291,9 +346,21 @@ static int launch_scaled_mm(const CUtensorMap& tw, const CUtensorMap& ta, Scaled
   return check_launch("scaled_mm_tc5_kernel");
 }
 
+template <typename T, int KIND>
+static int launch_scaled_mm(const CUtensorMap& tw, const CUtensorMap& ta, ScaledMMParams& p, dim3 grid, int nsub,
+                            cudaStream_t st) {
+  return nsub == 2 ? launch_scaled_mm_n<T, KIND, 2>(tw, ta, p, grid, st) : launch_scaled_mm_n<T, KIND, 1>(tw, ta, p, grid, st);
+}
+
 }  // namespace b200
 
 using namespace b200;
+
+extern "C" int b200_scaled_mm_set_tile(int tile) {
+  const int prev = g_smm_tile;
+  g_smm_tile = (tile == 1 || tile == 2) ? tile : 0;
+  return prev;
+}
 
 extern "C" int b200_scaled_mm_plan(int size_m, int size_n, int size_k) {
   if (size_m <= 0 || size_n <= 0 || size_k <= 0) return 1;
@@ -322,8 +389,9 @@ extern "C" int b200_cutlass_scaled_mm(void* out, const void* a, const void* b, c
   if (size_m == 0) return 0;
   const int toks = std::min(size_m, SM_TOK);
   const int box_rows = std::max(16, (toks + 15) & ~15);
+  const int nsub = scaled_mm_nsub(size_n);
   CUtensorMap tw, ta;
-  if (int rc = encode_u8_map(&tw, b, size_n, size_k, ldb, SM_NT)) return rc;
+  if (int rc = encode_u8_map(&tw, b, size_n, size_k, ldb, SM_NT * nsub)) return rc;
   if (int rc = encode_u8_map(&ta, a, size_m, size_k, lda, box_rows)) return rc;
   ScaledMMParams p{};
   p.c = out; p.a_scales = a_scales; p.b_scales = b_scales; p.bias = bias;
@@ -338,17 +406,23 @@ extern "C" int b200_cutlass_scaled_mm(void* out, const void* a, const void* b, c
   if (split_k <= 0) split_k = plan_scaled_mm_split(size_m, size_n, size_k);
   split_k = std::max(1, std::min(std::min(split_k, 8), chunks));
   if (workspace == nullptr) split_k = 1;                    // no scratch: one CTA per tile walks the whole k range
+  // the split reduction moves 4 channels per lane: 16-byte slab loads, 8-byte output stores
+  if (size_n % 4 != 0 || ldc % 4 != 0 || (reinterpret_cast<uintptr_t>(out) & 7) != 0 ||
+      (reinterpret_cast<uintptr_t>(workspace) & 15) != 0 || (reinterpret_cast<uintptr_t>(b_scales) & 15) != 0 ||
+      (bias != nullptr && (reinterpret_cast<uintptr_t>(bias) & 7) != 0))
+    split_k = 1;
   while (split_k > 1 && (split_k - 1) * ((chunks + split_k - 1) / split_k) >= chunks) --split_k;
   p.split_k = split_k;
   p.chunks_per_split = (chunks + split_k - 1) / split_k;
   p.scratch = reinterpret_cast<uint32_t*>(workspace);
   B200_CHECK(split_k == 1 || (reinterpret_cast<uintptr_t>(workspace) & 3) == 0, "scaled_mm workspace must be 4-byte aligned");
-  dim3 grid((size_n + SM_NT - 1) / SM_NT, (size_m + SM_TOK - 1) / SM_TOK, split_k);
+  const int cta_ch = SM_NT * nsub;
+  dim3 grid((size_n + cta_ch - 1) / cta_ch, (size_m + SM_TOK - 1) / SM_TOK, split_k);
   cudaStream_t st = (cudaStream_t)stream;
   if (ab_dtype == B200_AB_FP8_E4M3) {
-    if (out_dtype == B200_BF16) return launch_scaled_mm<__nv_bfloat16, SMK_FP8>(tw, ta, p, grid, st);
-    return launch_scaled_mm<__half, SMK_FP8>(tw, ta, p, grid, st);
+    if (out_dtype == B200_BF16) return launch_scaled_mm<__nv_bfloat16, SMK_FP8>(tw, ta, p, grid, nsub, st);
+    return launch_scaled_mm<__half, SMK_FP8>(tw, ta, p, grid, nsub, st);
   }
-  if (out_dtype == B200_BF16) return launch_scaled_mm<__nv_bfloat16, SMK_INT8>(tw, ta, p, grid, st);
-  return launch_scaled_mm<__half, SMK_INT8>(tw, ta, p, grid, st);
+  if (out_dtype == B200_BF16) return launch_scaled_mm<__nv_bfloat16, SMK_INT8>(tw, ta, p, grid, nsub, st);
+  return launch_scaled_mm<__half, SMK_INT8>(tw, ta, p, grid, nsub, st);
 }

@@ -280,6 +280,29 @@ def test_scaled_mm_k_splits_are_bit_identical(cabi):
             torch.testing.assert_close(o.cpu().float(), ref.float(), atol=2 ** -6, rtol=2 ** -7)
 
 
+@pytest.mark.parametrize("mnk", [(256, 6144, 4096), (48, 384, 1024), (300, 4096, 2048), (16, 128, 512)])
+def test_scaled_mm_tile_shapes_agree(ops, cabi, mnk):
+    """128- and 256-channel CTA tiles (b200_scaled_mm_set_tile) are two schedules of the same arithmetic: int8 results are
+    bit-identical, fp8 results agree to fp32 re-association of the k-split partial sums."""
+    M, N, K = mnk
+    try:
+        for kind in ("int8", "fp8"):
+            a, w = _mm_inputs(M, N, K, kind, seed=5)
+            sa = torch.rand(M, 1, generator=torch.Generator().manual_seed(1)) + 0.5
+            sb = (torch.rand(N, 1, generator=torch.Generator().manual_seed(2)) + 0.5) * (1.0 / K if kind == "fp8" else 1.0 / (K * 64))
+            outs = []
+            for tile in (1, 2):
+                cabi.b200_scaled_mm_set_tile(tile)
+                outs.append(ops.cutlass_scaled_mm(a.to(DEV), w.to(DEV).t(), sa.to(DEV), sb.to(DEV), torch.bfloat16).cpu())
+            if kind == "int8":
+                assert torch.equal(outs[0], outs[1])
+            ref = f_rows.scaled_mm(a, w.t(), sa, sb, torch.bfloat16)
+            for o in outs:
+                torch.testing.assert_close(o.float(), ref.float(), atol=2 ** -6, rtol=2 ** -7)
+    finally:
+        cabi.b200_scaled_mm_set_tile(0)
+
+
 def test_scaled_mm_strided_operands_and_errors(ops):
     M, N, K = 40, 256, 512
     a, w = _mm_inputs(M, N, K + 128, "fp8", seed=2)
