@@ -296,22 +296,58 @@ static int encode_u8_map(CUtensorMap* tmap, const void* base, int64_t rows, int 
   return 0;
 }
 
-// channels per CTA: 256 (two sub-tiles share one activation tile) whenever the matrix has more than one 128-channel
-// tile; b200_scaled_mm_set_tile() overrides for A-B measurement (0 = auto, 1 = 128, 2 = 256)
+// channels per CTA: 256 (two sub-tiles share one activation tile) when the 128-channel tiling would need more than one
+// wave of the SMs — there the kernel runs at the L2 -> SM fabric rate and the shared activation tile cuts that traffic
+// by a third (4096 x 28672 at 256 tokens: 71.7 -> 61.9 us); with fewer tiles the k-split fills the GPU and wider tiles
+// only mean more slabs to reduce (4096 x 4096: 23.6 us at 128 channels, 53.2 us at 256; profiles/r02_bench_f_rows.json).
+// b200_scaled_mm_set_tile() overrides for A-B measurement (0 = auto, 1 = 128, 2 = 256).
 static thread_local int g_smm_tile = 0;
-static int scaled_mm_nsub(int N) {
+static int scaled_mm_nsub(int M, int N) {
   if (g_smm_tile == 1) return 1;
   if (g_smm_tile == 2) return 2;
-  return N > SM_NT ? 2 : 1;
+  const int tiles = ((N + SM_NT - 1) / SM_NT) * ((M + SM_TOK - 1) / SM_TOK);
+  return tiles > num_sms() ? 2 : 1;
 }
 
-// k-splits of one tile: enough to fill one wave of the SMs, at least 4 chunks (512 k) each, at most 8 (portable cluster)
+// how many clusters of `split` CTAs of this kernel (one CTA per SM: ~200 KB of shared memory) the device holds at once.
+// A cluster lives inside one GPC, so the answer is sum over GPCs of floor(SMs / split), not SMs / split: 48 tiles x 3
+// splits = 144 CTAs "fit" 148 SMs but not their GPCs, and the clusters left over ran as a second wave.
+static int smm_max_active_clusters(int split) {
+  static thread_local int cache[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  if (split < 2 || split > 8) return 1 << 30;
+  if (cache[split] == 0) {
+    auto kern = scaled_mm_tc5_kernel<__nv_bfloat16, SMK_FP8, 1>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_SMEM_TOTAL);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(1, 1, (unsigned)split);
+    cfg.blockDim = dim3(SM_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = SM_SMEM_TOTAL - 1024;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = (unsigned)split;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) {
+      cudaGetLastError();
+      n = num_sms() / split;        // no device (plan queries on a CPU box) or no answer: the arithmetic bound
+    }
+    cache[split] = n;
+  }
+  return cache[split];
+}
+
+// k-splits of one tile: enough to fill one wave of the SMs (and of the GPCs' cluster slots), at least 4 chunks (512 k)
+// each, at most 8 (portable cluster)
 static int plan_scaled_mm_split(int M, int N, int K) {
-  const int cta_ch = SM_NT * scaled_mm_nsub(N);
+  const int cta_ch = SM_NT * scaled_mm_nsub(M, N);
   const int tiles = ((N + cta_ch - 1) / cta_ch) * ((M + SM_TOK - 1) / SM_TOK);
   const int chunks = (K + SM_KC - 1) / SM_KC;
   int split = std::min(std::min(num_sms() / std::max(tiles, 1), chunks / 4), 8);
   if (split < 1) split = 1;
+  while (split > 1 && tiles > smm_max_active_clusters(split)) --split;
   while (split > 1 && (split - 1) * ((chunks + split - 1) / split) >= chunks) --split;     // never an empty split
   return split;
 }
@@ -389,7 +425,7 @@ extern "C" int b200_cutlass_scaled_mm(void* out, const void* a, const void* b, c
   if (size_m == 0) return 0;
   const int toks = std::min(size_m, SM_TOK);
   const int box_rows = std::max(16, (toks + 15) & ~15);
-  const int nsub = scaled_mm_nsub(size_n);
+  const int nsub = scaled_mm_nsub(size_m, size_n);
   CUtensorMap tw, ta;
   if (int rc = encode_u8_map(&tw, b, size_n, size_k, ldb, SM_NT * nsub)) return rc;
   if (int rc = encode_u8_map(&ta, a, size_m, size_k, lda, box_rows)) return rc;

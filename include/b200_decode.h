@@ -324,8 +324,9 @@ int b200_dynamic_per_token_scaled_fp8_quant(void* out, const void* input, float*
 enum { B200_AB_FP8_E4M3 = 0, B200_AB_INT8 = 1 };
 int b200_cutlass_scaled_mm_supports_fp8(int cuda_device_capability);
 int b200_scaled_mm_plan(int size_m, int size_n, int size_k);
-/* channels per CTA of the following launches on this host thread (tests / A-B measurement): 0 = auto (256 whenever
- * N > 128: two 128-channel sub-tiles share one activation tile), 1 = 128, 2 = 256. Returns the previous value. */
+/* channels per CTA of the following launches on this host thread (tests / A-B measurement): 0 = auto (256 — two
+ * 128-channel sub-tiles sharing one activation tile — when the 128-channel tiling exceeds one wave of the SMs, else
+ * 128 with a k-split), 1 = 128, 2 = 256. Returns the previous value. */
 int b200_scaled_mm_set_tile(int tile);
 int b200_cutlass_scaled_mm(void* out, const void* a, const void* b, const float* a_scales, const float* b_scales,
                            const void* bias, int size_m, int size_n, int size_k, int64_t lda, int64_t ldb,
