@@ -7,7 +7,7 @@ import re
 import subprocess
 import sys
 
-INTEREST = ("LDGMC", "UTCHMMA", "UTCMMA", "UTCBAR", "UTMALDG", "UTMASTG", "UBLKCP", "LDTM", "STTM", "UTCATOM", "HMMA", "LDSM",
+INTEREST = ("LDGMC", "UTCHMMA", "UTCQMMA", "UTCIMMA", "UTCMMA", "UTCBAR", "UTMALDG", "UTMASTG", "UBLKCP", "LDTM", "STTM", "UTCATOM", "HMMA", "LDSM",
             "MOVM", "SYNCS", "UCGABAR", "CGABAR", "MULTIMEM", "RED", "MEMBAR", "ERRBAR", "F2FP", "LDGSTS", "ELECT", "MAPA",
             "ACQBULK", "BAR", "ATOMG", "UTCCP", "CCTL")
 
