@@ -22,6 +22,38 @@ _WORLD_SIZES = (2, 4, 6, 8)
 _RANK_DATA_BYTES = 8 * 1024 * 1024
 
 
+def _physical_ids(visible_indices):
+    """CUDA-visible device indices -> NVML indices (CUDA_VISIBLE_DEVICES may renumber; UUID entries cannot be mapped)."""
+    import os
+    env = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if not env:
+        return list(visible_indices)
+    table = [int(t) for t in env.split(",") if t.strip().isdigit()]
+    if len(table) != len([t for t in env.split(",") if t.strip()]):
+        raise ValueError("CUDA_VISIBLE_DEVICES holds non-numeric entries")
+    return [table[i] for i in visible_indices]
+
+
+def _is_full_nvlink(visible_indices) -> bool:
+    """True iff NVML reports an NVLink P2P path between EVERY pair of the group's devices (the reference's rule,
+    device_communicators/custom_all_reduce.py:_is_full_nvlink). Any failure to find out means False: the caller then
+    keeps NCCL beyond two ranks instead of assuming a fabric that may not exist."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            handles = [pynvml.nvmlDeviceGetHandleByIndex(i) for i in _physical_ids(visible_indices)]
+            for i, a in enumerate(handles):
+                for b in handles[i + 1:]:
+                    if pynvml.nvmlDeviceGetP2PStatus(a, b, pynvml.NVML_P2P_CAPS_INDEX_NVLINK) != pynvml.NVML_P2P_STATUS_OK:
+                        return False
+            return True
+        finally:
+            pynvml.nvmlShutdown()
+    except Exception:
+        return False
+
+
 def is_weak_contiguous(inp: torch.Tensor) -> bool:
     """Contiguous, or a view that covers its storage's tail exactly (what the IPC registration can address)."""
     if inp.is_contiguous():
@@ -35,7 +67,7 @@ class CustomAllreduce:
     _ops = ops      # op table (a checker may substitute the reference's own kernels behind the same protocol)
 
     def __init__(self, group: ProcessGroup, device: Union[int, str, torch.device], max_size: int = 8192 * 1024,
-                 full_nvlink: bool = True) -> None:
+                 full_nvlink: Optional[bool] = None) -> None:
         self._IS_CAPTURING = False
         self.disabled = True
         self.group = group
@@ -45,10 +77,22 @@ class CustomAllreduce:
         if self.world_size not in _WORLD_SIZES:          # includes the single-rank case
             return
         self.device = torch.device(f"cuda:{device}") if isinstance(device, int) else torch.device(device)
+        # The decision to take the peer-memory path must be the SAME on every rank (a rank that returned early would
+        # leave the others blocked in the IPC exchange below), and it concerns the GROUP's devices, not every GPU this
+        # process can see: gather the ranks' device indices, test P2P among exactly those, then agree.
         here = self.device.index
-        if not all(torch.cuda.can_device_access_peer(here, other)
-                   for other in range(torch.cuda.device_count()) if other != here):
-            return                                       # no P2P between some pair: leave it to NCCL
+        peers = self._gather(here)
+        visible = torch.cuda.device_count()
+        local_ok = all(0 <= d < visible for d in peers) and len(set(peers)) == len(peers) and all(
+            torch.cuda.can_device_access_peer(here, d) for d in peers if d != here)
+        if full_nvlink is None:                          # like the reference: ask NVML about every pair of the group
+            full_nvlink = _is_full_nvlink(peers) if local_ok else False
+        decisions = self._gather((bool(local_ok), bool(full_nvlink)))
+        if not all(ok for ok, _ in decisions):
+            return                                       # no P2P between some pair: leave it to NCCL (on all ranks)
+        full_nvlink = all(nv for _, nv in decisions)
+        if self.world_size > 2 and not full_nvlink:
+            return                                       # > 2 PCIe-only GPUs: the reference falls back to NCCL as well
         self.max_size = max_size
         self.full_nvlink = full_nvlink
         self.meta = torch.zeros(self._ops.meta_size() + max_size, dtype=torch.uint8, device=self.device)
@@ -65,13 +109,17 @@ class CustomAllreduce:
         shared = t.untyped_storage()._share_cuda_()      # (device, handle, size, offset, ...)
         return shared[1], shared[3]
 
-    def _exchange(self, handle, offset):
-        """All-gather of one (handle, offset) pair per rank over the CPU group, in rank order."""
+    def _gather(self, obj):
+        """All-gather of one picklable object per rank over the CPU group, in rank order."""
         slots = [[None] for _ in range(self.world_size)]
-        slots[self.rank][0] = (handle, offset)
+        slots[self.rank][0] = obj
         for i, src in enumerate(sorted(dist.get_process_group_ranks(group=self.group))):
             dist.broadcast_object_list(slots[i], src=src, group=self.group, device="cpu")
-        pairs = [slot[0] for slot in slots]
+        return [slot[0] for slot in slots]
+
+    def _exchange(self, handle, offset):
+        """All-gather of one (handle, offset) pair per rank, in rank order."""
+        pairs = self._gather((handle, offset))
         return [h for h, _ in pairs], [o for _, o in pairs]
 
     def register_buffer(self, inp: torch.Tensor):

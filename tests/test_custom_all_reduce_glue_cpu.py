@@ -57,15 +57,25 @@ class _Torch:
         return torch.empty(*a, **k)
 
 
-def _make(monkeypatch, world, rank, peers_ok=True, **kw):
+def _make(monkeypatch, world, rank, peers_ok=True, peer_devices=None, peer_decision=(True, True), nvlink=True, **kw):
     ops, tp = _Ops(), _Torch(peers_ok)
     monkeypatch.setattr(car, "ops", ops)
     monkeypatch.setattr(car.CustomAllreduce, "_ops", ops)
     monkeypatch.setattr(car, "torch", tp)
+    monkeypatch.setattr(car, "_is_full_nvlink", lambda devices: nvlink)
+    calls = {"n": 0}
 
     def bcast(lst, src, group=None, device=None):
+        # gathers happen in a fixed order: device indices, (p2p ok, nvlink) decisions, then IPC (handle, offset) pairs
+        phase = calls["n"] // world
+        calls["n"] += 1
         if lst[0] is None:
-            lst[0] = (f"peer{src}".encode(), 1000 + src)
+            if phase == 0:
+                lst[0] = (peer_devices or list(range(world)))[src] if src != rank else 1
+            elif phase == 1:
+                lst[0] = peer_decision
+            else:
+                lst[0] = (f"peer{src}".encode(), 1000 + src)
 
     monkeypatch.setattr(car, "dist", types.SimpleNamespace(
         get_backend=lambda g: "gloo", Backend=dist.Backend, get_rank=lambda group=None: rank,
@@ -73,7 +83,8 @@ def _make(monkeypatch, world, rank, peers_ok=True, **kw):
         broadcast_object_list=bcast))
     monkeypatch.setattr(torch.UntypedStorage, "_share_cuda_", lambda self: (0, b"mine", 0, 64, 0, 0, 0, 0),
                         raising=False)
-    return car.CustomAllreduce("cpu-group", "cuda:1", max_size=1 << 16, **kw), ops, tp
+    devs = peer_devices or list(range(world))
+    return car.CustomAllreduce("cpu-group", f"cuda:{devs[rank] if rank < len(devs) else 0}", max_size=1 << 16, **kw), ops, tp
 
 
 @pytest.mark.parametrize("world", [1, 3, 5, 16])
@@ -85,6 +96,31 @@ def test_unsupported_world_sizes_stay_disabled(monkeypatch, world):
 def test_missing_peer_access_disables(monkeypatch):
     ca, ops, _ = _make(monkeypatch, 2, 0, peers_ok=False)
     assert ca.disabled and ops.calls == []
+
+
+def test_decision_is_taken_over_the_groups_devices_and_agreed_by_all_ranks(monkeypatch):
+    """the P2P gate looks at the GROUP's devices and every rank takes the same decision."""
+    ca, ops, _ = _make(monkeypatch, 2, 0, peer_decision=(False, True))      # the peer cannot reach us: we stand down too
+    assert ca.disabled and ops.calls == []
+    ca, ops, _ = _make(monkeypatch, 2, 0, peer_devices=[0, 9])              # a peer's device index this process cannot see
+    assert ca.disabled and ops.calls == []
+    ca, ops, _ = _make(monkeypatch, 4, 1, nvlink=False)                     # 4 PCIe-only GPUs: NCCL, like the reference
+    assert ca.disabled and ops.calls == []
+    ca, ops, _ = _make(monkeypatch, 2, 1, nvlink=False)                     # 2 ranks without NVLink still take the kernel
+    assert not ca.disabled and ops.calls[0][-1] is False
+    ca, ops, _ = _make(monkeypatch, 4, 2, peer_decision=(True, False))      # a peer saw no NVLink: nobody assumes it
+    assert ca.disabled
+
+
+def test_physical_id_mapping(monkeypatch):
+    monkeypatch.delenv("CUDA_VISIBLE_DEVICES", raising=False)
+    assert car._physical_ids([0, 2]) == [0, 2]
+    monkeypatch.setenv("CUDA_VISIBLE_DEVICES", "4,5,6,7")
+    assert car._physical_ids([0, 3]) == [4, 7]
+    monkeypatch.setenv("CUDA_VISIBLE_DEVICES", "GPU-abc,1")
+    with pytest.raises(ValueError):
+        car._physical_ids([0])
+    assert car._is_full_nvlink([0]) in (True, False)                        # never raises, with or without NVML / a GPU
 
 
 def test_construction_exchanges_ipc_pairs_in_rank_order(monkeypatch):

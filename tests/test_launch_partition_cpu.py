@@ -189,3 +189,25 @@ def test_python_restatement_equals_the_library_plan():
         if M <= 32:
             expect = max(expect, small_partition(N, K, 148)[1])
         assert lib.b200_marlin_gemm_plan(M, N, K, groups) == expect, (M, N, K, gs)
+
+
+def test_scaled_mm_split_plan_properties():
+    """W8A8 GEMM k-split plan (csrc/scaled_mm.cu, queried through the C ABI on a CPU box: no device, so the cluster-slot
+    bound falls back to SMs / split): 1 <= split <= 8, never an empty split, at least 4 chunks (512 k) per split, never
+    more CTAs than one wave, and the tile-shape override only changes the tile count it plans for."""
+    from aphrodite_engine_b200 import _native
+    lib = _native.load_c_abi()
+    try:
+        for tile in (0, 1, 2):
+            lib.b200_scaled_mm_set_tile(tile)
+            for M in (1, 16, 256, 300, 4096):
+                for N in (64, 128, 4096, 6144, 28672):
+                    for K in (128, 512, 1040, 4096, 14336):
+                        split = lib.b200_scaled_mm_plan(M, N, K)
+                        chunks = (K + 127) // 128
+                        assert 1 <= split <= 8 and split <= max(1, chunks // 4)
+                        per = (chunks + split - 1) // split
+                        assert (split - 1) * per < chunks, (M, N, K, split)
+        assert lib.b200_scaled_mm_plan(0, 128, 128) == 1 and lib.b200_scaled_mm_plan(16, 128, 0) == 1
+    finally:
+        assert lib.b200_scaled_mm_set_tile(0) in (0, 1, 2)
