@@ -83,7 +83,7 @@ __device__ __forceinline__ uint4 load_cache8(const void* src, float scale) {
 }
 
 template <typename T, int DT, int KV>
-__global__ void __launch_bounds__(PF_THREADS, (DT == 8 ? 3 : 1)) prefill_attention_kernel(const PrefillParams p) {
+__global__ void __launch_bounds__(PF_THREADS, (DT == 8 || DT == 4 ? 3 : 1)) prefill_attention_kernel(const PrefillParams p) {
   constexpr int D = DT * 16;
   constexpr int KSTR = D + 8;                                  // elements per K / new-V row (+16 B pad)
   constexpr int K_TILE = PF_BN * KSTR;                         // elements
@@ -257,14 +257,14 @@ __global__ void __launch_bounds__(PF_THREADS, (DT == 8 ? 3 : 1)) prefill_attenti
     // tiles that lie entirely inside the context / strictly below the causal diagonal need no mask at all
     const bool plain = !has_alibi && sw <= 0 && (is_ctx ? (tile_start + PF_BN <= ctx_len) : (tile - n_ctx < mt));
     if (plain) {
+      // the scale folds into the exponent's FMA below; the row maximum of the scaled logits is the scaled maximum
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          s[nt][e] *= scale2;
-          mx[e >> 1] = fmaxf(mx[e >> 1], s[nt][e]);
-        }
+        for (int e = 0; e < 4; ++e) mx[e >> 1] = fmaxf(mx[e >> 1], s[nt][e]);
       }
+      mx[0] *= scale2;
+      mx[1] *= scale2;
     } else {
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
@@ -296,19 +296,24 @@ __global__ void __launch_bounds__(PF_THREADS, (DT == 8 ? 3 : 1)) prefill_attenti
       l_run[h] *= alpha[h];
     }
     uint32_t pa[4][4];
+    const float ps = plain ? scale2 : 1.f;                     // masked tiles hold scaled logits already
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-      const float p0 = ex2(s[nt][0] - msafe[0]), p1 = ex2(s[nt][1] - msafe[0]);
-      const float p2 = ex2(s[nt][2] - msafe[1]), p3 = ex2(s[nt][3] - msafe[1]);
+      const float p0 = ex2(fmaf(s[nt][0], ps, -msafe[0])), p1 = ex2(fmaf(s[nt][1], ps, -msafe[0]));
+      const float p2 = ex2(fmaf(s[nt][2], ps, -msafe[1])), p3 = ex2(fmaf(s[nt][3], ps, -msafe[1]));
       l_run[0] += p0 + p1;
       l_run[1] += p2 + p3;
       pa[nt >> 1][(nt & 1) * 2 + 0] = pack2<T>(p0, p1);
       pa[nt >> 1][(nt & 1) * 2 + 1] = pack2<T>(p2, p3);
     }
+    // the running maximum stops moving after the first few tiles of a row: rescale the output accumulators only when
+    // some row of this warp needs it (warp-uniform branch)
+    if (__any_sync(0xffffffffu, alpha[0] != 1.f || alpha[1] != 1.f)) {
 #pragma unroll
-    for (int i = 0; i < 2 * DT; ++i) {
-      o[i][0] *= alpha[0]; o[i][1] *= alpha[0];
-      o[i][2] *= alpha[1]; o[i][3] *= alpha[1];
+      for (int i = 0; i < 2 * DT; ++i) {
+        o[i][0] *= alpha[0]; o[i][1] *= alpha[0];
+        o[i][2] *= alpha[1]; o[i][3] *= alpha[1];
+      }
     }
 
     // ---- O += P . V ------------------------------------------------------------------------------------------------

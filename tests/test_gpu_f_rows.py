@@ -441,3 +441,51 @@ def test_sampling_vs_reference_kernels(ops, ref):
     torch.testing.assert_close(a[rows], b[rows], rtol=2e-5, atol=1e-9)
     logits = torch.randn(B, V, device=DEV)
     assert torch.equal(ops.top_k_mask_logits(logits, None, 100), ref.top_k_mask_logits(logits, None, 100))
+
+
+# ====================================================================================================== CUDA graphs
+def test_f_rows_are_cuda_graph_capturable(ops):
+    """Decode and prefill run under torch.cuda.graph in the reference (worker/model_runner.py:1682+): the W8A8 GEMM (k-split
+    path: scratch from the caching allocator, cluster launch), the quantiser, a rejection sampler and the prefill attention
+    are captured once and replayed on new inputs in the same buffers."""
+    from aphrodite_engine_b200.attention.prefix_prefill import context_attention_fwd
+    g = torch.Generator().manual_seed(0)
+    M, N, K = 64, 512, 4096                                       # 4 tiles -> k-split cluster
+    x = torch.randn(M, K, generator=g).to(torch.bfloat16).to(DEV)
+    w8, sw = ops.scaled_fp8_quant((torch.randn(N, K, generator=g) * 0.05).to(torch.bfloat16).to(DEV), use_per_token_if_dynamic=True)
+    probs = torch.softmax(torch.randn(8, 4000, generator=g) * 3, -1).to(DEV)
+    uni = torch.rand(32, 8, generator=g).to(DEV)
+    d = _make_prefill_case(torch.bfloat16, 4, 2, 128, 16, [40, 7], [50, 64], "auto", 8, seed=3)
+    dd = {k: (v.to(DEV) if isinstance(v, torch.Tensor) else v) for k, v in d.items()}
+    o = torch.empty_like(dd["q"])
+    out = {}
+
+    def step():
+        a8, sa = ops.scaled_fp8_quant(x, use_per_token_if_dynamic=True)
+        out["mm"] = ops.cutlass_scaled_mm(a8, w8.t(), sa, sw, torch.bfloat16)
+        out["ids"], out["ok"] = ops.top_k_sampling_from_probs(probs, uni, None, 10)
+        context_attention_fwd(dd["q"], dd["k"], dd["v"], o, "auto", dd["key_cache"], dd["value_cache"], dd["block_tables"],
+                              dd["start_loc"], dd["seq_lens"], dd["ctx_lens"], 64)
+
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        step()
+        st.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=st):
+            step()
+    # new inputs in the captured buffers
+    x.copy_(torch.randn(M, K, generator=g).to(torch.bfloat16))
+    probs.copy_(torch.softmax(torch.randn(8, 4000, generator=g) * 3, -1))
+    dd["q"].copy_((torch.randn(dd["q"].shape, generator=g) * 0.5).to(torch.bfloat16))
+    graph.replay()
+    torch.cuda.synchronize()
+    a8, sa = f_rows.dynamic_per_token_scaled_fp8_quant(x.cpu())
+    ref = f_rows.scaled_mm(a8, w8.cpu().t(), sa, sw.cpu(), torch.bfloat16)
+    torch.testing.assert_close(out["mm"].cpu().float(), ref.float(), atol=2 ** -6, rtol=2 ** -7)
+    rid, rok, marg = f_rows.rejection_sampling("top_k", probs.cpu().numpy(), uni.cpu().numpy(), k=10)
+    sure = marg > MARGIN
+    assert (out["ids"].cpu().numpy()[sure] == rid[sure]).all()
+    refo = f_rows.context_attention(dd["q"].cpu(), d["k"], d["v"], d["key_cache"], d["value_cache"], d["block_tables"],
+                                    d["start_loc"], d["seq_lens"], d["ctx_lens"])
+    torch.testing.assert_close(o.cpu().float(), refo.float(), atol=1e-2, rtol=1e-2)
