@@ -61,9 +61,13 @@ __global__ void __launch_bounds__(512) fp8_quant_tensor_kernel(uint8_t* __restri
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t step = (int64_t)gridDim.x * blockDim.x;
   if (vec_ok(in, out, numel)) {
-    for (int64_t i = tid * 8; i < numel; i += step * 8) {
-      float f[8];
+    // two 16-byte loads in flight per thread and iteration
+    for (int64_t i = tid * 8; i < numel; i += step * 16) {
+      const int64_t i2 = i + step * 8;
+      const bool two = i2 < numel;
+      float f[8], g[8];
       load8(in + i, f);
+      if (two) load8(in + i2, g);
       uint32_t lo = 0, hi = 0;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -71,6 +75,15 @@ __global__ void __launch_bounds__(512) fp8_quant_tensor_kernel(uint8_t* __restri
         hi |= (uint32_t)to_e4m3_mul(f[4 + j], inv) << (8 * j);
       }
       *reinterpret_cast<uint2*>(out + i) = make_uint2(lo, hi);
+      if (two) {
+        lo = 0; hi = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          lo |= (uint32_t)to_e4m3_mul(g[j], inv) << (8 * j);
+          hi |= (uint32_t)to_e4m3_mul(g[4 + j], inv) << (8 * j);
+        }
+        *reinterpret_cast<uint2*>(out + i2) = make_uint2(lo, hi);
+      }
     }
   } else {
     for (int64_t i = tid; i < numel; i += step) out[i] = to_e4m3_mul(to_f32<T>(in[i]), inv);
