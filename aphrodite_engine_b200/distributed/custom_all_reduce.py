@@ -36,22 +36,33 @@ def _physical_ids(visible_indices):
 
 def _is_full_nvlink(visible_indices) -> bool:
     """True iff NVML reports an NVLink P2P path between EVERY pair of the group's devices (the reference's rule,
-    device_communicators/custom_all_reduce.py:_is_full_nvlink). Any failure to find out means False: the caller then
-    keeps NCCL beyond two ranks instead of assuming a fabric that may not exist."""
+    device_communicators/custom_all_reduce.py:_is_full_nvlink). A definite "no" from NVML means False (beyond two ranks
+    the caller then keeps NCCL, as the reference does on PCIe-only boxes). When NVML cannot be asked at all (module
+    missing, no permission in the container, UUID-style CUDA_VISIBLE_DEVICES) the answer falls back to what the caller
+    already established — peer access between every pair — and says so."""
     try:
         import pynvml
         pynvml.nvmlInit()
+    except Exception as e:
+        import warnings
+        warnings.warn(f"NVML unavailable ({e!r}): assuming the peer-accessible devices are NVLink-connected")
+        return True
+    try:
+        handles = [pynvml.nvmlDeviceGetHandleByIndex(i) for i in _physical_ids(visible_indices)]
+        for i, a in enumerate(handles):
+            for b in handles[i + 1:]:
+                if pynvml.nvmlDeviceGetP2PStatus(a, b, pynvml.NVML_P2P_CAPS_INDEX_NVLINK) != pynvml.NVML_P2P_STATUS_OK:
+                    return False
+        return True
+    except Exception as e:
+        import warnings
+        warnings.warn(f"NVML query failed ({e!r}): assuming the peer-accessible devices are NVLink-connected")
+        return True
+    finally:
         try:
-            handles = [pynvml.nvmlDeviceGetHandleByIndex(i) for i in _physical_ids(visible_indices)]
-            for i, a in enumerate(handles):
-                for b in handles[i + 1:]:
-                    if pynvml.nvmlDeviceGetP2PStatus(a, b, pynvml.NVML_P2P_CAPS_INDEX_NVLINK) != pynvml.NVML_P2P_STATUS_OK:
-                        return False
-            return True
-        finally:
             pynvml.nvmlShutdown()
-    except Exception:
-        return False
+        except Exception:
+            pass
 
 
 def is_weak_contiguous(inp: torch.Tensor) -> bool:

@@ -88,3 +88,43 @@ def test_tensor_parallel_split_world2_gloo():
         assert a, f"rank {rank}: head-sharded attention differs"
         assert m, f"rank {rank}: row-parallel MLP + all-reduce differs"
         assert t, f"rank {rank}: sharded greedy token differs"
+
+
+def _car_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import aphrodite_engine_b200.distributed.custom_all_reduce as car
+        # rank 1 pretends it cannot reach its peer; rank 0 believes everything is fine: BOTH must stand down, and
+        # neither may be left waiting in the IPC exchange that follows the decision
+        calls = []
+        car.torch = type("T", (), {"__getattr__": lambda self, n: getattr(torch, n)})()
+        car.torch.cuda = type("C", (), {"device_count": staticmethod(lambda: 2),
+                                        "can_device_access_peer": staticmethod(lambda a, b: rank == 0)})()
+        car._is_full_nvlink = lambda devs: True
+        ca = car.CustomAllreduce(dist.group.WORLD, f"cuda:{rank}")
+        gathered = ca._gather(("hello", rank))
+        q.put((rank, ca.disabled, gathered == [("hello", 0), ("hello", 1)], calls))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_custom_allreduce_enable_decision_is_collective_world2_gloo():
+    """The peer-memory all-reduce's enable decision over REAL torch.distributed (gloo): an asymmetric peer-access answer
+    disables the communicator on every rank and the constructor returns on all of them (the old per-rank
+    early return left the other ranks blocked in broadcast_object_list)."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_car_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=150) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    for rank, disabled, gather_ok, _ in res:
+        assert disabled, f"rank {rank} enabled the peer path although rank 1 has no peer access"
+        assert gather_ok, f"rank {rank}: object all-gather out of rank order"
