@@ -129,3 +129,33 @@ def test_reshape_and_cache_matches_live_reference_exact():
         rcache.reshape_and_cache(key, value, kc, vc, slots, "auto", 1.0, 1.0)
         po.reshape_and_cache(key, value, kc2, vc2, slots)
         assert torch.equal(kc, kc2) and torch.equal(vc, vc2)
+
+
+@needs_ref
+def test_baseline_config0_opt125m_fp32_decode_loop_matches_live_reference():
+    """BASELINE.json configs[0] — facebook/opt-125m, fp32, CPU backend, bs = 1, seq = 128 — at the attention layer's
+    shape (12 heads, MHA, head 64, block 16): the reference's own CPU kernels are driven token by token (cache write,
+    then paged attention over the tokens so far), and the restatement must follow every step."""
+    _, rcache, _ = ref_lib.load()
+    torch.manual_seed(125)
+    H, D, BS, SEQ = 12, 64, 16, 128
+    NB = SEQ // BS + 2
+    scale = D ** -0.5
+    kc = torch.zeros(NB, H, D // 4, BS, 4)                  # fp32: x = 16 B / 4 B = 4 elements per run
+    vc = torch.zeros(NB, H, D, BS)
+    kc2, vc2 = kc.clone(), vc.clone()
+    table = torch.randperm(NB)[: SEQ // BS].to(torch.int32).view(1, -1)
+    worst = 0.0
+    for t in range(SEQ):
+        k_new, v_new = torch.randn(1, H, D) * 0.3, torch.randn(1, H, D) * 0.3
+        q = torch.empty(1, H, D).uniform_(-scale, scale)
+        slot = torch.tensor([int(table[0, t // BS]) * BS + t % BS])
+        rcache.reshape_and_cache(k_new, v_new, kc, vc, slot, "auto", 1.0, 1.0)
+        po.reshape_and_cache(k_new, v_new, kc2, vc2, slot)
+        sl = torch.tensor([t + 1], dtype=torch.int32)
+        out = torch.empty_like(q)
+        ref_lib.paged_attention_v1(out, q, kc, vc, H, scale, table, sl, BS, t + 1)
+        mine = po.paged_attention(q, kc2, vc2, table, sl, scale)
+        worst = max(worst, float((mine - out).abs().max()))
+    assert torch.equal(kc, kc2) and torch.equal(vc, vc2)
+    assert worst <= 1e-5, worst
