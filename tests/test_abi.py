@@ -223,3 +223,23 @@ def test_ops_refuse_cpu_tensors():
     x = torch.randn(2, 8)
     with pytest.raises((NotImplementedError, RuntimeError)):
         ops.silu_and_mul(torch.empty(2, 4), x)
+
+
+def test_header_is_plain_c_and_every_symbol_links(tmp_path):
+    """include/b200_decode.h is the drop-in boundary for NON-torch hosts (cgo / JNI / ctypes stubs): it must compile as
+    plain C99 and every declared function must resolve against libb200decode.so at link time."""
+    from aphrodite_engine_b200 import _native
+    syms = sorted(_declared_symbols())
+    src = tmp_path / "link_all.c"
+    body = "\n".join(f"    p[{i}] = (fn_t)&{s};" for i, s in enumerate(syms))
+    src.write_text('#include "b200_decode.h"\n#include <stdio.h>\ntypedef void (*fn_t)(void);\nint main(void) {\n'
+                   f"    fn_t p[{len(syms)}];\n{body}\n"
+                   f'    printf("%d %d\\n", b200_abi_version(), (int)(sizeof p / sizeof p[0]));\n    return p[0] == 0;\n}}\n')
+    exe = tmp_path / "link_all"
+    libdir = os.path.dirname(_native.LIB_PATH)
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", f"-I{os.path.join(ROOT, 'include')}", str(src),
+                        "-o", str(exe), f"-L{libdir}", "-lb200decode", f"-Wl,-rpath,{libdir}"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.split() == ["1", str(len(syms))], (out.stdout, out.stderr)
